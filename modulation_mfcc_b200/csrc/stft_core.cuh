@@ -1,0 +1,244 @@
+// Per-thread phases of the fused frame -> window -> real FFT -> |X|^2 path.
+//
+// Replaces the librosa stft under script/mfcc.py:387 (reference) for one frame.
+// A frame of NFFT real samples is packed as M = NFFT/2 complex points
+// z[c] = x[2c] + i*x[2c+1]; TPF = M/16 threads own 16 points each and run a
+// mixed-radix Cooley-Tukey transform 16 x R2 x R3 with the data in registers and
+// one shared-memory exchange between passes; a final split step turns Z into
+// the real-input spectrum X[0..M] and stores |X|^2.
+//
+// Index algebra (all indices per frame; tau = thread within the frame):
+//   n  = n1 + TPF*n2            n1 = tau,  n2 = 0..15      (register index)
+//   pass 1: 16-pt DFT over n2 -> k2;  twiddle W_M^{n1*k2}
+//   n1 = m1 + R3*m2             m1 < R3,   m2 < R2
+//   pass 2: R2-pt DFT over m2 -> j2; twiddle W_TPF^{m1*j2}
+//   pass 3: R3-pt DFT over m1 -> j1
+//   k  = 16*(R2*j1 + j2) + k2
+//
+// Every phase is __host__ __device__: tests/emu/ runs the same code thread by
+// thread on the CPU against numpy's rfft, so the index algebra is checked
+// without a GPU.
+#pragma once
+#include "fft_regs.cuh"
+
+namespace mmf {
+
+template <int NFFT>
+struct FftCfg {
+  static_assert(NFFT >= 256 && NFFT <= 4096 && (NFFT & (NFFT - 1)) == 0, "n_fft must be a power of two in [256, 4096]");
+  static constexpr int N = NFFT;
+  static constexpr int M = NFFT / 2;          // complex points
+  static constexpr int F = M + 1;             // real-spectrum bins
+  static constexpr int TPF = M / 16;          // threads per frame
+  static constexpr int R2 = TPF < 16 ? TPF : 16;
+  static constexpr int R3 = TPF / R2;         // 1, 2, 4, 8
+  static constexpr int NB2 = 16 / R2;         // pass-2 butterflies per thread
+  static constexpr int NB3 = 16 / R3;         // pass-3 butterflies per thread
+  static constexpr int PITCH1 = TPF + R3;     // exchange-1 row pitch (float2), conflict-free reads
+  static constexpr int PITCH2 = 16 + 16 / R3; // exchange-2 row pitch (float2)
+  static constexpr int X1 = 16 * PITCH1;
+  static constexpr int X2 = R3 > 1 ? 16 * R3 * PITCH2 : 0;
+  static constexpr int XZ = M;                // natural-order Z for the split step
+  static constexpr int XBUF = (X1 > X2 ? (X1 > XZ ? X1 : XZ) : (X2 > XZ ? X2 : XZ));  // float2 per frame slot
+  static constexpr int TW1 = 16 * TPF;        // float2: W_M^{n1*k2} at [k2*TPF + n1]
+  static constexpr int TW2 = 16 * R3;         // float2: W_TPF^{m1*j2} at [j2*R3 + m1]
+};
+
+// e^{-2*pi*i*r/32}, r = 0..8
+MMF_HD float2 w32(int r) {
+  constexpr float c[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                          0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
+                          0.19509032201612825f, 0.0f};
+  return make_float2(c[r], -c[8 - r]);
+}
+
+// ---- phase L: gather 16 strided complex points of the frame and apply the window
+// span: PCM of the tile in shared memory; frame starts at span[frame_off].
+// wreg[n2] = 0.5 * (w[2c], w[2c+1]) with c = tau + TPF*n2 (the 0.5 is the 1/2 of
+// the real-FFT split step, folded in exactly).
+template <int NFFT, bool VEC>
+MMF_HD void ph_load(float2 (&v)[16], const float* span, int frame_off, int tau, const float2 (&wreg)[16]) {
+  using C = FftCfg<NFFT>;
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int c = tau + C::TPF * n2;
+    float2 x;
+    if constexpr (VEC) {
+      x = *reinterpret_cast<const float2*>(span + frame_off + 2 * c);
+    } else {
+      x.x = span[frame_off + 2 * c];
+      x.y = span[frame_off + 2 * c + 1];
+    }
+    v[n2] = make_float2(x.x * wreg[n2].x, x.y * wreg[n2].y);
+  }
+}
+
+// ---- pass 1: 16-point DFT over n2 and the W_M^{n1*k2} twiddle
+template <int NFFT>
+MMF_HD void ph_pass1(float2 (&v)[16], const float2* tw1, int tau) {
+  using C = FftCfg<NFFT>;
+  dft16(v);
+#pragma unroll
+  for (int k2 = 1; k2 < 16; ++k2) v[k2] = cmul(v[k2], tw1[k2 * C::TPF + tau]);
+}
+
+// ---- exchange 1: A'[n1][k2] at xb[k2*PITCH1 + n1]
+template <int NFFT>
+MMF_HD void ph_x1_write(const float2 (&v)[16], float2* xb, int tau) {
+  using C = FftCfg<NFFT>;
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) xb[k2 * C::PITCH1 + tau] = v[k2];
+}
+
+// thread tau' = m1 + R3*kq reads n1 = m1 + R3*m2, k2 = kq + R2*u into v[u*R2 + m2]
+template <int NFFT>
+MMF_HD void ph_x1_read(float2 (&v)[16], const float2* xb, int tau) {
+  using C = FftCfg<NFFT>;
+  const int m1 = tau % C::R3, kq = tau / C::R3;
+#pragma unroll
+  for (int u = 0; u < C::NB2; ++u)
+#pragma unroll
+    for (int m2 = 0; m2 < C::R2; ++m2)
+      v[u * C::R2 + m2] = xb[(kq + C::R2 * u) * C::PITCH1 + m1 + C::R3 * m2];
+}
+
+// ---- pass 2: NB2 butterflies of radix R2 over m2 -> j2, twiddle W_TPF^{m1*j2}
+template <int NFFT>
+MMF_HD void ph_pass2(float2 (&v)[16], const float2* tw2, int tau) {
+  using C = FftCfg<NFFT>;
+  dft_groups<C::R2, C::NB2>(v);
+  if constexpr (C::R3 > 1) {
+    const int m1 = tau % C::R3;
+#pragma unroll
+    for (int j2 = 1; j2 < 16; ++j2) v[j2] = cmul(v[j2], tw2[j2 * C::R3 + m1]);
+  }
+}
+
+// ---- exchange 2 (R3 > 1 only; R2 == 16, u == 0, kq == k2):
+// B'[m1][j2][k2] at xb[(j2*R3 + m1)*PITCH2 + k2]
+template <int NFFT>
+MMF_HD void ph_x2_write(const float2 (&v)[16], float2* xb, int tau) {
+  using C = FftCfg<NFFT>;
+  const int m1 = tau % C::R3, k2 = tau / C::R3;
+#pragma unroll
+  for (int j2 = 0; j2 < 16; ++j2) xb[(j2 * C::R3 + m1) * C::PITCH2 + k2] = v[j2];
+}
+
+// thread tau'' = k2 + 16*jq reads j2 = jq + R3*e, all m1, into v[e*R3 + m1]
+template <int NFFT>
+MMF_HD void ph_x2_read(float2 (&v)[16], const float2* xb, int tau) {
+  using C = FftCfg<NFFT>;
+  const int k2 = tau % 16, jq = tau / 16;
+#pragma unroll
+  for (int e = 0; e < C::NB3; ++e)
+#pragma unroll
+    for (int m1 = 0; m1 < C::R3; ++m1)
+      v[e * C::R3 + m1] = xb[((jq + C::R3 * e) * C::R3 + m1) * C::PITCH2 + k2];
+}
+
+template <int NFFT>
+MMF_HD void ph_pass3(float2 (&v)[16]) {
+  using C = FftCfg<NFFT>;
+  dft_groups<C::R3, C::NB3>(v);
+}
+
+// ---- natural-order store of Z for the split step: z[k], k = 16*(R2*j1 + j2) + k2
+template <int NFFT>
+MMF_HD void ph_z_write(const float2 (&v)[16], float2* xb, int tau) {
+  using C = FftCfg<NFFT>;
+  if constexpr (C::R3 > 1) {
+    const int k2 = tau % 16, jq = tau / 16;
+#pragma unroll
+    for (int e = 0; e < C::NB3; ++e)
+#pragma unroll
+      for (int j1 = 0; j1 < C::R3; ++j1) {
+        const int j2 = jq + C::R3 * e;
+        xb[16 * (C::R2 * j1 + j2) + k2] = v[e * C::R3 + j1];
+      }
+  } else {
+    const int kq = tau;  // m1 == 0
+#pragma unroll
+    for (int u = 0; u < C::NB2; ++u)
+#pragma unroll
+      for (int j2 = 0; j2 < C::R2; ++j2) xb[16 * j2 + kq + C::R2 * u] = v[u * C::R2 + j2];
+  }
+}
+
+// ---- split step for one conjugate pair: a = Z[k], b = Z[(M-k) mod M] (both
+// already scaled by 1/2 through the window).  Returns (|X[k]|^2, |X[M-k]|^2).
+// wk = e^{-2*pi*i*k/NFFT} is applied as c32[r] (compile-time) then wtau.
+MMF_HD float2 split_pair(float2 a, float2 b, float2 c32r, float2 wtau) {
+  const float2 E = make_float2(a.x + b.x, a.y - b.y);
+  const float2 O = make_float2(a.y + b.y, b.x - a.x);
+  const float2 WO = cmul(cmul(O, c32r), wtau);
+  const float2 Xp = cadd(E, WO), Xm = csub(E, WO);
+  return make_float2(Xp.x * Xp.x + Xp.y * Xp.y, Xm.x * Xm.x + Xm.y * Xm.y);
+}
+
+// ---- split step from the natural-order buffer (any NFFT).
+// Thread tau handles k = tau + TPF*r, r = 0..7 (covers [0, M/2)); tau == 0 also k = M/2.
+// Power lands in ptile[k*ppitch + t].
+template <int NFFT>
+MMF_HD void ph_split_smem(const float2* xb, float* ptile, int ppitch, int t, int tau, float2 wtau) {
+  using C = FftCfg<NFFT>;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int k = tau + C::TPF * r;
+    const float2 a = xb[k];
+    const float2 b = xb[(C::M - k) & (C::M - 1)];
+    const float2 p = split_pair(a, b, w32(r), wtau);
+    ptile[k * ppitch + t] = p.x;
+    ptile[(C::M - k) * ppitch + t] = p.y;
+  }
+  if (tau == 0) {
+    const float2 a = xb[C::M / 2];
+    const float2 p = split_pair(a, a, w32(8), wtau);
+    ptile[(C::M / 2) * ppitch + t] = p.x;
+  }
+}
+
+// ---- split step for NFFT == 512 straight from registers.  After pass 2 thread
+// s = tau holds Z[16*j2 + s] in v[j2].  bpart[r] must hold Z[M - (16*r + s)]:
+// on the device it is v[15 - r] of lane (16 - s) & 15 (one shuffle per float);
+// for s == 0 it is the thread's own v[(16 - r) & 15].
+MMF_HD void ph_split_regs512(const float2 (&v)[16], const float2 (&bpart)[8], float* ptile, int ppitch, int t,
+                             int s, float2 wtau) {
+  constexpr int M = 256;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int k = 16 * r + s;
+    const float2 p = split_pair(v[r], bpart[r], w32(r), wtau);
+    ptile[k * ppitch + t] = p.x;
+    ptile[(M - k) * ppitch + t] = p.y;
+  }
+  if (s == 0) {
+    const float2 p = split_pair(v[8], v[8], w32(8), wtau);
+    ptile[(M / 2) * ppitch + t] = p.x;
+  }
+}
+
+// ---- mel projection of one frame column from the power tile, for bands
+// [m0, m1).  The Slaney filterbank (script/mfcc.py:387 -> librosa.filters.mel)
+// is stored sparsely: bin k lies in segment seg(k) (between two filter centres)
+// and feeds at most filter seg-1 (falling slope, w2[k].x) and filter seg
+// (rising slope, w2[k].y).  seg_start[j] = first bin of segment j.
+// Calls emit(m, value) for every band.
+template <typename Emit>
+MMF_HD void mel_column(const float* ptile, int ppitch, int t, const int* seg_start, const float2* w2, int m0, int m1,
+                       Emit emit) {
+  float up_prev = 0.0f;
+  for (int j = m0; j <= m1; ++j) {
+    const int k0 = seg_start[j], k1 = seg_start[j + 1];
+    float acc_dn = 0.0f, acc_up = 0.0f;
+    for (int k = k0; k < k1; ++k) {
+      const float p = ptile[k * ppitch + t];
+      const float2 w = w2[k];
+      acc_dn = fmaf(w.x, p, acc_dn);
+      acc_up = fmaf(w.y, p, acc_up);
+    }
+    if (j > m0) emit(j - 1, up_prev + acc_dn);
+    up_prev = acc_up;
+  }
+}
+
+}  // namespace mmf
