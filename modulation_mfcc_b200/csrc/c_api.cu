@@ -1,0 +1,729 @@
+// extern "C" surface of libmmf_b200.so (declared in include/mmf.h).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cudaTypedefs.h>
+
+#include "mmf_internal.h"
+
+namespace mmf {
+
+static thread_local std::string g_err;
+static thread_local long g_launches = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches += n; }
+
+static int fail(int code, const std::string& msg) {
+  set_error(msg);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  return fail(MMF_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define MMF_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+static int validate_cfg(const mmf_config* c) {
+  if (!c) return fail(MMF_ERR_INVALID, "config is NULL");
+  if (c->n_fft < 256 || c->n_fft > 4096 || (c->n_fft & (c->n_fft - 1)))
+    return fail(MMF_ERR_UNSUPPORTED, "n_fft must be a power of two in [256, 4096]");
+  if (c->win_length < 1 || c->win_length > c->n_fft)
+    return fail(MMF_ERR_INVALID, "Target size (n_fft) must be at least input size (win_length)");
+  if (c->hop_length < 1) return fail(MMF_ERR_INVALID, "hop_length must be a positive integer");
+  if (c->n_mels < 1 || c->n_mels > 512) return fail(MMF_ERR_UNSUPPORTED, "n_mels must be in [1, 512]");
+  if (c->n_mfcc < 1 || c->n_mfcc > 128 || c->n_mfcc > c->n_mels)
+    return fail(MMF_ERR_UNSUPPORTED, "n_mfcc must be in [1, min(128, n_mels)]");
+  if (!(c->sample_rate > 0)) return fail(MMF_ERR_INVALID, "sample_rate must be positive");
+  if (!(c->fmax > c->fmin) || c->fmin < 0) return fail(MMF_ERR_INVALID, "need 0 <= fmin < fmax");
+  return MMF_OK;
+}
+
+template <typename T>
+static cudaError_t upload(T** dst, const std::vector<T>& src) {
+  cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(1, src.size()) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static int ensure_ws(mmf_plan* p, size_t bytes) {
+  if (bytes <= p->ws_bytes) return MMF_OK;
+  if (p->ws) {
+    MMF_CUDA(cudaDeviceSynchronize());
+    MMF_CUDA(cudaFree(p->ws));
+    p->ws = nullptr;
+    p->ws_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&p->ws, bytes);
+  if (e != cudaSuccess) return fail(MMF_ERR_NOMEM, std::string("workspace cudaMalloc: ") + cudaGetErrorString(e));
+  p->ws_bytes = bytes;
+  return MMF_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// carve `bytes` out of a bump pointer
+static void* carve(unsigned char*& cur, size_t bytes) {
+  void* r = cur;
+  cur += align_up(bytes, 256);
+  return r;
+}
+
+static int fill_sos(const double* sos, int n_sections, SosArgs* a) {
+  if (n_sections < 1 || n_sections > 16) return fail(MMF_ERR_UNSUPPORTED, "n_sections must be in [1, 16]");
+  a->n_sections = n_sections;
+  std::memset(a->sos, 0, sizeof(a->sos));
+  std::memset(a->zi, 0, sizeof(a->zi));
+  for (int s = 0; s < n_sections; ++s)
+    for (int k = 0; k < 6; ++k) a->sos[s][k] = sos[6 * s + k] / (k == 3 ? 1.0 : sos[6 * s + 3]);
+  double zi[32];
+  int padlen = 0;
+  if (host_sos_zi(sos, n_sections, zi, &padlen) != 0) return fail(MMF_ERR_INVALID, "singular SOS section");
+  for (int s = 0; s < n_sections; ++s) {
+    a->zi[s][0] = zi[2 * s];
+    a->zi[s][1] = zi[2 * s + 1];
+  }
+  a->padlen = padlen;
+  return MMF_OK;
+}
+
+}  // namespace mmf
+
+using namespace mmf;
+
+extern "C" {
+
+int mmf_version(void) { return MMF_VERSION; }
+const char* mmf_last_error(void) { return g_err.c_str(); }
+int64_t mmf_launch_count(int32_t reset) {
+  const long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int64_t mmf_num_frames(int64_t n_samples, int32_t n_fft, int32_t hop_length) {
+  if (hop_length < 1) return -1;
+  const int64_t padded = n_samples + 2 * (int64_t)(n_fft / 2);
+  if (padded < n_fft) return 0;
+  return 1 + (padded - n_fft) / hop_length;
+}
+
+int mmf_host_tables(const mmf_config* cfg, float* window, float* mel, float* dct) {
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  const int F = cfg->n_fft / 2 + 1;
+  if (window) {
+    std::vector<float> w;
+    host_window(cfg->win_length, cfg->n_fft, w);
+    std::memcpy(window, w.data(), w.size() * sizeof(float));
+  }
+  if (mel) {
+    std::vector<float> m;
+    std::vector<double> mf;
+    host_mel_dense(cfg->sample_rate, cfg->n_fft, cfg->n_mels, cfg->fmin, cfg->fmax, m, mf);
+    std::memcpy(mel, m.data(), (size_t)cfg->n_mels * F * sizeof(float));
+  }
+  if (dct) {
+    std::vector<float> d;
+    host_dct(cfg->n_mfcc, cfg->n_mels, d);
+    std::memcpy(dct, d.data(), d.size() * sizeof(float));
+  }
+  return MMF_OK;
+}
+
+int mmf_sos_zi(const double* sos, int32_t n_sections, double* zi, int32_t* padlen) {
+  if (!sos || !zi) return fail(MMF_ERR_INVALID, "NULL argument");
+  int pl = 0;
+  if (host_sos_zi(sos, n_sections, zi, &pl) != 0) return fail(MMF_ERR_INVALID, "bad SOS cascade");
+  if (padlen) *padlen = pl;
+  return MMF_OK;
+}
+
+int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
+  if (!out) return fail(MMF_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(MMF_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                  cudaGetErrorString(ce));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MMF_ERR_INVALID, "device ordinal out of range");
+  MMF_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  MMF_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10)
+    return fail(MMF_ERR_UNSUPPORTED, "this library is built for sm_100a (Blackwell B200) only");
+
+  mmf_plan* p = new mmf_plan();
+  p->cfg = *cfg;
+  p->F = cfg->n_fft / 2 + 1;
+  p->sm_count = prop.multiProcessorCount;
+  stft_geometry(cfg->n_fft, &p->geo);
+  p->lead = cfg->preemph != 0.0f ? 2 : 0;
+
+  // ---- tile geometry: largest TF (multiple of frames/iteration, power of two <= 32)
+  // whose shared memory lets two CTAs share an SM; otherwise the smallest TF.
+  const int fpi = p->geo.fpi;
+  const int fpw = p->geo.tpf < 32 ? 32 / p->geo.tpf : 1;  // frames per warp in the FFT phase
+  auto pitch_for = [&](int tf) {
+    int pp = std::max(tf, fpw);
+    if (fpw == 1) {
+      if ((pp & 1) == 0) ++pp;
+    } else {
+      pp = (pp + fpw - 1) / fpw * fpw;
+      if (((pp / fpw) & 1) == 0) pp += fpw;
+    }
+    return pp;
+  };
+  auto smem_for = [&](int tf, int pt_bufs) {
+    const int span = (tf - 1) * cfg->hop_length + cfg->n_fft + p->lead + 3;
+    const int alloc = (span + 255) / 256 * 256;
+    return stft_smem_bytes(cfg->n_fft, alloc, pitch_for(tf), pt_bufs, cfg->n_mels);
+  };
+  // two CTAs per SM need <= 113 KB each (227 KB per SM, 1 KB reserved per CTA)
+  const size_t budget2 = 113 * 1024, budget1 = 226 * 1024;
+  int tf = 0, pt_bufs = 2, ctas = 2;
+  for (int cand = 32; cand >= fpi && tf == 0; cand >>= 1) {
+    if (cand % fpi) continue;
+    if (smem_for(cand, 2) <= budget2) {
+      tf = cand;
+      pt_bufs = 2;
+    } else if (smem_for(cand, 1) <= budget2) {
+      tf = cand;
+      pt_bufs = 1;
+    }
+  }
+  if (tf == 0) {
+    ctas = 1;
+    tf = std::min(32, fpi);
+    pt_bufs = smem_for(tf, 2) <= budget1 ? 2 : 1;
+    if (fpi > 32 || smem_for(tf, pt_bufs) > budget1) {
+      delete p;
+      return fail(MMF_ERR_UNSUPPORTED, "hop_length/n_fft combination needs more shared memory than one SM has");
+    }
+  }
+  p->TF = tf;
+  p->pt_bufs = pt_bufs;
+  p->ctas_per_sm = ctas;
+  p->ppitch = pitch_for(tf);
+  p->smem = smem_for(tf, pt_bufs);
+  const int workers = 8 * (32 / tf);
+  p->bands_per_worker = (cfg->n_mels + workers - 1) / workers;
+
+  // ---- constant tables
+  std::vector<float> window, mel, dct;
+  std::vector<double> mel_f;
+  host_window(cfg->win_length, cfg->n_fft, window);
+  host_mel_dense(cfg->sample_rate, cfg->n_fft, cfg->n_mels, cfg->fmin, cfg->fmax, mel, mel_f);
+  MelSparse sp;
+  if (!host_mel_sparse(mel, mel_f, cfg->sample_rate, cfg->n_fft, cfg->n_mels, sp)) {
+    delete p;
+    return fail(MMF_ERR_UNSUPPORTED, "mel filterbank is not a two-slope (triangular) bank");
+  }
+  host_dct(cfg->n_mfcc, cfg->n_mels, dct);
+  std::vector<float2> tw1, tw2;
+  host_twiddles(cfg->n_fft, p->geo, tw1, tw2);
+  p->nc_pad = cfg->n_mfcc <= 16 ? 16 : (cfg->n_mfcc <= 32 ? 32 : (cfg->n_mfcc <= 64 ? 64 : 128));
+  std::vector<float> dct_pad((size_t)cfg->n_mels * p->nc_pad, 0.0f);
+  for (int k = 0; k < cfg->n_mfcc; ++k)
+    for (int m = 0; m < cfg->n_mels; ++m) dct_pad[(size_t)m * p->nc_pad + k] = dct[(size_t)k * cfg->n_mels + m];
+  std::vector<float2> w2(p->F);
+  for (int k = 0; k < p->F; ++k) w2[k] = make_float2(sp.w2[2 * k], sp.w2[2 * k + 1]);
+
+  cudaError_t e;
+  if ((e = upload(&p->d_window, window)) != cudaSuccess || (e = upload(&p->d_tw1, tw1)) != cudaSuccess ||
+      (e = upload(&p->d_tw2, tw2)) != cudaSuccess || (e = upload(&p->d_seg, sp.seg_start)) != cudaSuccess ||
+      (e = upload(&p->d_w2, w2)) != cudaSuccess || (e = upload(&p->d_dct, dct_pad)) != cudaSuccess) {
+    mmf_plan_destroy(p);
+    return cuda_fail(e, "uploading plan constants");
+  }
+
+  // ---- driver entry point for tensor-map encoding (no link-time libcuda dependency)
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) p->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&p->events[i], cudaEventDisableTiming);
+  *out = p;
+  return MMF_OK;
+}
+
+int mmf_plan_destroy(mmf_plan* p) {
+  if (!p) return MMF_OK;
+  cudaSetDevice(p->cfg.device);
+  cudaDeviceSynchronize();
+  cudaFree(p->d_window);
+  cudaFree(p->d_tw1);
+  cudaFree(p->d_tw2);
+  cudaFree(p->d_seg);
+  cudaFree(p->d_w2);
+  cudaFree(p->d_dct);
+  cudaFree(p->ws);
+  if (p->pinned) cudaFreeHost(p->pinned);
+  for (int i = 0; i < 2; ++i)
+    if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+  for (int i = 0; i < 4; ++i)
+    if (p->events[i]) cudaEventDestroy(p->events[i]);
+  delete p;
+  return MMF_OK;
+}
+
+}  // extern "C"
+
+namespace mmf {
+
+// shared body of mmf_stft_power / mmf_logmel
+static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                    float* power, float* logmel, int* clipmax, cudaStream_t st) {
+  if (!p) return fail(MMF_ERR_INVALID, "plan is NULL");
+  if (!pcm) return fail(MMF_ERR_INVALID, "pcm is NULL");
+  if (n_clips < 1 || n_samples < 1) return fail(MMF_ERR_INVALID, "n_clips and n_samples must be positive");
+  if (clip_stride < n_samples && n_clips > 1) return fail(MMF_ERR_INVALID, "clip_stride < n_samples");
+  if (logmel && !clipmax) return fail(MMF_ERR_INVALID, "clipmax buffer required with logmel");
+  const mmf_config& c = p->cfg;
+  const int64_t T = mmf_num_frames(n_samples, c.n_fft, c.hop_length);
+  if (T < 1) return fail(MMF_ERR_INVALID, "input too short for one frame");
+  if (T > 0x7fffffff || n_samples + c.n_fft > 0x7fffffffLL)
+    return fail(MMF_ERR_UNSUPPORTED, "clip longer than 2^31 samples");
+  MMF_CUDA(cudaSetDevice(c.device));
+
+  StftArgs a{};
+  a.pcm = pcm;
+  a.n_samples = n_samples;
+  a.clip_stride = clip_stride;
+  a.T = (int)T;
+  a.hop = c.hop_length;
+  a.TF = p->TF;
+  a.tiles_per_clip = (int)((T + p->TF - 1) / p->TF);
+  a.n_tiles = (long)a.tiles_per_clip * n_clips;
+  a.lead = p->lead;
+  a.span_floats = (p->TF - 1) * c.hop_length + c.n_fft + p->lead + 3;  // +3: 16-byte aligned start
+  a.span_alloc = (a.span_floats + 255) / 256 * 256;
+  a.ppitch = p->ppitch;
+  a.pt_bufs = p->pt_bufs;
+  a.vec_ok = (c.hop_length % 2 == 0) ? 1 : 0;
+  a.split_regs = (c.n_fft == 512 && !(c.flags & MMF_FLAG_SPLIT_SMEM)) ? 1 : 0;
+  a.n_mels = c.n_mels;
+  a.bands_per_worker = p->bands_per_worker;
+  a.amin = c.amin;
+  a.preemph = c.preemph;
+  a.window = p->d_window;
+  a.tw1 = p->d_tw1;
+  a.tw2 = p->d_tw2;
+  a.seg_start = p->d_seg;
+  a.w2 = p->d_w2;
+  a.logmel = logmel;
+  a.clipmax = clipmax;
+  a.power = power;
+
+  // TMA needs a 16-byte aligned base and row pitch; otherwise use the plain loader
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  bool tma = p->encode != nullptr && !(c.flags & MMF_FLAG_NO_TMA) && ((uintptr_t)pcm % 16 == 0) &&
+             ((clip_stride * 4) % 16 == 0 || n_clips == 1);
+  if (tma) {
+    cuuint64_t gdim[2] = {(cuuint64_t)n_samples, (cuuint64_t)n_clips};
+    cuuint64_t gstr[1] = {(cuuint64_t)(n_clips == 1 ? align_up((size_t)n_samples * 4, 16) : clip_stride * 4)};
+    cuuint32_t box[2] = {256, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = p->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)pcm, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) tma = false;
+  }
+  a.use_tma = tma ? 1 : 0;
+
+  if (clipmax) {
+    cudaError_t e = fill_i32_launch(clipmax, n_clips, (int)0x80800000, st)  /* key of -FLT_MAX */;
+    if (e != cudaSuccess) return cuda_fail(e, "clipmax init");
+  }
+  const long max_ctas = (long)p->ctas_per_sm * p->sm_count;
+  const int grid = (int)std::min<long>(a.n_tiles, max_ctas);
+  cudaError_t e = stft_mel_launch(c.n_fft, tmap, a, grid, p->smem, st);
+  count_launch();
+  if (e != cudaSuccess) return cuda_fail(e, "stft_mel_kernel launch");
+  return MMF_OK;
+}
+
+}  // namespace mmf
+
+extern "C" {
+
+int mmf_stft_power(mmf_plan* plan, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                   float* power_dev, void* stream) {
+  if (!power_dev) return fail(MMF_ERR_INVALID, "power_dev is NULL");
+  return run_stft(plan, pcm_dev, n_clips, n_samples, clip_stride, power_dev, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int mmf_logmel(mmf_plan* plan, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+               float* logmel_dev, int32_t* clipmax_dev, void* stream) {
+  if (!logmel_dev) return fail(MMF_ERR_INVALID, "logmel_dev is NULL");
+  return run_stft(plan, pcm_dev, n_clips, n_samples, clip_stride, nullptr, logmel_dev, clipmax_dev,
+                  (cudaStream_t)stream);
+}
+
+int mmf_mfcc(mmf_plan* plan, float* logmel_dev, const int32_t* clipmax_dev, int64_t n_clips, int64_t T,
+             float* mfcc_dev, float* delta_dev, int32_t clamp_in_place, void* stream) {
+  if (!plan || !logmel_dev || !clipmax_dev || !mfcc_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_clips < 1 || T < 1) return fail(MMF_ERR_INVALID, "n_clips and T must be positive");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  for (int64_t c0 = 0; c0 < n_clips; c0 += 65535) {
+    const int64_t nc = std::min<int64_t>(65535, n_clips - c0);
+    cudaError_t e = mfcc_launch(plan->d_dct, plan->nc_pad, logmel_dev + (size_t)c0 * plan->cfg.n_mels * T,
+                                clipmax_dev + c0, nc, T, plan->cfg.n_mels, plan->cfg.n_mfcc, plan->cfg.top_db,
+                                mfcc_dev + (size_t)c0 * plan->cfg.n_mfcc * T,
+                                delta_dev ? delta_dev + (size_t)c0 * plan->cfg.n_mfcc * T : nullptr, clamp_in_place,
+                                (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "mfcc_kernel launch");
+  }
+  return MMF_OK;
+}
+
+int mmf_sosfiltfilt(mmf_plan* plan, const void* x_dev, int32_t x_is_f32, int64_t rows, int64_t T,
+                    int64_t x_row_stride, const double* sos_host, int32_t n_sections, double* y_dev,
+                    int64_t y_row_stride, void* stream) {
+  if (!plan || !x_dev || !sos_host || !y_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (rows < 1) return fail(MMF_ERR_INVALID, "rows must be positive");
+  SosArgs a;
+  int rc = fill_sos(sos_host, n_sections, &a);
+  if (rc) return rc;
+  if (T <= a.padlen) {
+    char buf[128];
+    std::snprintf(buf, sizeof(buf), "The length of the input vector x must be greater than padlen, which is %d.",
+                  a.padlen);
+    return fail(MMF_ERR_TOO_SHORT, buf);
+  }
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  cudaError_t e = sosfiltfilt_launch(x_dev, x_is_f32, rows, T, x_row_stride, a, y_dev, y_row_stride,
+                                     (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "sosfiltfilt_kernel launch");
+  return MMF_OK;
+}
+
+int mmf_delta_norm(mmf_plan* plan, const double* x_dev, int64_t n_clips, int32_t rows_per_clip, int64_t T,
+                   int32_t method, double* tot_dev, void* stream) {
+  if (!plan || !x_dev || !tot_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_clips < 1 || rows_per_clip < 1 || T < 1) return fail(MMF_ERR_INVALID, "sizes must be positive");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  for (int64_t c0 = 0; c0 < n_clips; c0 += 65535) {
+    const int64_t nc = std::min<int64_t>(65535, n_clips - c0);
+    cudaError_t e = delta_norm_launch(x_dev + (size_t)c0 * rows_per_clip * T, nc, rows_per_clip, T, method,
+                                      tot_dev + (size_t)c0 * T, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "delta_norm_kernel launch");
+  }
+  return MMF_OK;
+}
+
+// small host arrays are staged through the plan workspace tail (first 64 KB reserved)
+static int stage_consts(mmf_plan* plan, const void* host, size_t bytes, size_t offset, void** dev, cudaStream_t st) {
+  int rc = ensure_ws(plan, std::max<size_t>(plan->ws_bytes, 1 << 20));
+  if (rc) return rc;
+  if (offset + bytes > (64 << 10)) return fail(MMF_ERR_UNSUPPORTED, "coefficient arrays larger than 64 KB");
+  *dev = (unsigned char*)plan->ws + offset;
+  MMF_CUDA(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, st));
+  return MMF_OK;
+}
+
+int mmf_fir_filtfilt(mmf_plan* plan, const double* x_dev, int64_t rows, int64_t T, const double* b_host,
+                     int32_t n_taps, double* y_dev, double* work_dev, void* stream) {
+  if (!plan || !x_dev || !b_host || !y_dev || !work_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_taps < 1 || n_taps > 4096) return fail(MMF_ERR_UNSUPPORTED, "n_taps must be in [1, 4096]");
+  if (rows < 1 || rows > 65535) return fail(MMF_ERR_UNSUPPORTED, "rows must be in [1, 65535]");
+  if (T <= 3 * n_taps) {
+    char buf[128];
+    std::snprintf(buf, sizeof(buf), "The length of the input vector x must be greater than padlen, which is %d.",
+                  3 * n_taps);
+    return fail(MMF_ERR_TOO_SHORT, buf);
+  }
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  void* b_dev = nullptr;
+  int rc = stage_consts(plan, b_host, (size_t)n_taps * 8, 0, &b_dev, (cudaStream_t)stream);
+  if (rc) return rc;
+  cudaError_t e = fir_filtfilt_launch(x_dev, rows, T, (const double*)b_dev, n_taps, y_dev, work_dev,
+                                      (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "fir kernels launch");
+  return MMF_OK;
+}
+
+int mmf_stencil(mmf_plan* plan, const double* x_dev, int64_t rows, int64_t T, const double* coef_host, int32_t half,
+                const double* edge_l_host, const double* edge_r_host, int32_t n_edge, int32_t n_edge_in,
+                double* y_dev, void* stream) {
+  if (!plan || !x_dev || !coef_host || !y_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (half < 0 || n_edge < half || n_edge_in < 0) return fail(MMF_ERR_INVALID, "need n_edge >= half >= 0");
+  if (n_edge > 0 && (!edge_l_host || !edge_r_host)) return fail(MMF_ERR_INVALID, "edge matrices are NULL");
+  if (T < n_edge_in || T < 2 * n_edge) return fail(MMF_ERR_TOO_SHORT, "input shorter than the stencil's edge window");
+  if (rows < 1 || rows > 65535) return fail(MMF_ERR_UNSUPPORTED, "rows must be in [1, 65535]");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t cb = (size_t)(2 * half + 1) * 8, eb = (size_t)n_edge * n_edge_in * 8;
+  void *c_dev = nullptr, *l_dev = nullptr, *r_dev = nullptr;
+  int rc = stage_consts(plan, coef_host, cb, 0, &c_dev, st);
+  if (rc) return rc;
+  if (eb) {
+    if ((rc = stage_consts(plan, edge_l_host, eb, align_up(cb, 256), &l_dev, st))) return rc;
+    if ((rc = stage_consts(plan, edge_r_host, eb, align_up(cb, 256) + align_up(eb, 256), &r_dev, st))) return rc;
+  }
+  cudaError_t e = stencil_launch(x_dev, rows, T, (const double*)c_dev, half, (const double*)l_dev,
+                                 (const double*)r_dev, n_edge, n_edge_in, y_dev, st);
+  if (e != cudaSuccess) return cuda_fail(e, "stencil_kernel launch");
+  return MMF_OK;
+}
+
+int mmf_modspec(mmf_plan* plan, const float* mfcc_dev, int64_t n_clips, int32_t n_coef, int64_t T, int32_t win,
+                int32_t hop, int32_t nfft, float* mag_dev, float* band_dev, const int32_t* band_lo_host,
+                const int32_t* band_hi_host, int32_t n_bands, void* stream) {
+  if (!plan || !mfcc_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (win < 1 || hop < 1 || nfft < win || nfft < 2 || nfft > 4096 || (nfft & (nfft - 1)))
+    return fail(MMF_ERR_UNSUPPORTED, "need 1 <= win <= nfft, nfft a power of two <= 4096, hop >= 1");
+  if (n_bands < 0 || n_bands > 16) return fail(MMF_ERR_UNSUPPORTED, "n_bands must be in [0, 16]");
+  if (band_dev && n_bands > 0 && (!band_lo_host || !band_hi_host)) return fail(MMF_ERR_INVALID, "band edges are NULL");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  void *lo = nullptr, *hi = nullptr;
+  if (band_dev && n_bands > 0) {
+    for (int b = 0; b < n_bands; ++b)
+      if (band_lo_host[b] < 0 || band_hi_host[b] > nfft / 2 + 1 || band_lo_host[b] > band_hi_host[b])
+        return fail(MMF_ERR_INVALID, "band bin range outside [0, nfft/2+1]");
+    int rc = stage_consts(plan, band_lo_host, (size_t)n_bands * 4, 0, &lo, st);
+    if (rc) return rc;
+    if ((rc = stage_consts(plan, band_hi_host, (size_t)n_bands * 4, 256, &hi, st))) return rc;
+  }
+  cudaError_t e = modspec_launch(mfcc_dev, n_clips, n_coef, T, win, hop, nfft, mag_dev,
+                                 (band_dev && n_bands > 0) ? band_dev : nullptr, (const int*)lo, (const int*)hi,
+                                 n_bands, st);
+  if (e != cudaSuccess) return cuda_fail(e, "modspec_kernel launch");
+  return MMF_OK;
+}
+
+int mmf_rms(mmf_plan* plan, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+            int32_t frame_length, int32_t hop_length, int32_t center, float* rms_dev, void* stream) {
+  if (!plan || !pcm_dev || !rms_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (frame_length < 1 || hop_length < 1) return fail(MMF_ERR_INVALID, "frame_length and hop_length must be positive");
+  const int pad = center ? frame_length / 2 : 0;
+  const int64_t padded = n_samples + 2 * (int64_t)pad;
+  if (padded < frame_length) return fail(MMF_ERR_TOO_SHORT, "Input is too short for frame_length");
+  const int64_t T = 1 + (padded - frame_length) / hop_length;
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  for (int64_t c0 = 0; c0 < n_clips; c0 += 65535) {
+    const int64_t nc = std::min<int64_t>(65535, n_clips - c0);
+    cudaError_t e = rms_launch(pcm_dev + (size_t)c0 * clip_stride, nc, n_samples, clip_stride, frame_length,
+                               hop_length, pad, T, rms_dev + (size_t)c0 * T, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "rms_kernel launch");
+  }
+  return MMF_OK;
+}
+
+}  // extern "C"
+
+namespace mmf {
+
+static size_t change_ws_bytes(const mmf_plan* p, int64_t n_clips, int64_t T, bool need_logmel, bool need_mfcc,
+                              int rows) {
+  size_t b = 64 << 10;
+  if (need_logmel) b += align_up((size_t)n_clips * p->cfg.n_mels * T * 4, 256);
+  b += align_up((size_t)n_clips * 4, 256);
+  if (need_mfcc) b += align_up((size_t)n_clips * p->cfg.n_mfcc * T * 4, 256);
+  b += align_up((size_t)n_clips * rows * T * 8, 256);
+  b += align_up((size_t)n_clips * T * 8, 256);
+  return b;
+}
+
+static int too_short(int padlen) {
+  char buf[128];
+  std::snprintf(buf, sizeof(buf), "The length of the input vector x must be greater than padlen, which is %d.", padlen);
+  return fail(MMF_ERR_TOO_SHORT, buf);
+}
+
+// log-mel -> clamp -> MFCC (+delta) -> zero-phase Butterworth per coefficient ->
+// derivative + norm -> output filter.  `cur` bumps through caller-provided workspace.
+static int run_post(mmf_plan* p, unsigned char*& cur, float* logmel, const int* clipmax, int64_t n_clips, int64_t T,
+                    const mmf_change_params* prm, double* tot, float* mfcc_out, float* delta_out, int clamp_in_place,
+                    cudaStream_t st) {
+  const mmf_config& c = p->cfg;
+  const int first = prm->remove_first ? 1 : 0;
+  const int rows = c.n_mfcc - first;
+  if (rows < 1) return fail(MMF_ERR_INVALID, "removeFirst leaves no MFCC rows");
+  SosArgs sa, so;
+  int rc = fill_sos(prm->sos, prm->n_sections, &sa);
+  if (rc) return rc;
+  if (prm->out_kind == 0 && (rc = fill_sos(prm->out_sos, prm->out_n_sections, &so))) return rc;
+  if (T <= sa.padlen) return too_short(sa.padlen);
+  if (prm->out_kind == 0 && T <= so.padlen) return too_short(so.padlen);
+  float* mfcc = mfcc_out ? mfcc_out : (float*)carve(cur, (size_t)n_clips * c.n_mfcc * T * 4);
+  double* filt = (double*)carve(cur, (size_t)n_clips * rows * T * 8);
+  double* raw = (double*)carve(cur, (size_t)n_clips * T * 8);
+  if ((rc = mmf_mfcc(p, logmel, clipmax, n_clips, T, mfcc, delta_out, clamp_in_place, st))) return rc;
+  // Butterworth zero-phase low-pass of rows first..n_mfcc-1 of every clip (script/mfcc.py:398-402)
+  cudaError_t e = sosfiltfilt_launch_grouped(mfcc + (size_t)first * T, 1, n_clips * rows, T, T, rows,
+                                             (long)c.n_mfcc * T, sa, filt, T, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sosfiltfilt (mfcc rows)");
+  double* change = prm->out_kind == 0 ? raw : tot;
+  if ((rc = mmf_delta_norm(p, filt, n_clips, rows, T, prm->diff_method, change, st))) return rc;
+  if (prm->out_kind == 0) {
+    e = sosfiltfilt_launch(raw, 0, n_clips, T, T, so, tot, T, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sosfiltfilt (total change)");
+  }
+  return MMF_OK;
+}
+
+// device-resident body; `base` is a workspace of change_ws_bytes()
+static int run_change(mmf_plan* p, unsigned char* base, const float* pcm, int64_t n_clips, int64_t n_samples,
+                      int64_t clip_stride, const mmf_change_params* prm, double* tot, float* logmel_out,
+                      float* mfcc_out, float* delta_out, cudaStream_t st) {
+  const mmf_config& c = p->cfg;
+  const int64_t T = mmf_num_frames(n_samples, c.n_fft, c.hop_length);
+  unsigned char* cur = base + (64 << 10);
+  float* logmel = logmel_out ? logmel_out : (float*)carve(cur, (size_t)n_clips * c.n_mels * T * 4);
+  int* clipmax = (int*)carve(cur, (size_t)n_clips * 4);
+  int rc;
+  if ((rc = run_stft(p, pcm, n_clips, n_samples, clip_stride, nullptr, logmel, clipmax, st))) return rc;
+  return run_post(p, cur, logmel, clipmax, n_clips, T, prm, tot, mfcc_out, delta_out, logmel_out ? 1 : 0, st);
+}
+
+}  // namespace mmf
+
+extern "C" {
+
+int mmf_mfcc_change(mmf_plan* plan, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                    const mmf_change_params* prm, double* tot_dev, float* logmel_dev, float* mfcc_dev,
+                    float* delta_dev, void* stream) {
+  if (!plan || !pcm_dev || !prm || !tot_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_clips < 1 || n_samples < 1) return fail(MMF_ERR_INVALID, "n_clips and n_samples must be positive");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  const int64_t T = mmf_num_frames(n_samples, plan->cfg.n_fft, plan->cfg.hop_length);
+  const int rows = plan->cfg.n_mfcc - (prm->remove_first ? 1 : 0);
+  const size_t need = change_ws_bytes(plan, n_clips, T, logmel_dev == nullptr, mfcc_dev == nullptr, std::max(rows, 1));
+  int rc = ensure_ws(plan, need);
+  if (rc) return rc;
+  return run_change(plan, (unsigned char*)plan->ws, pcm_dev, n_clips, n_samples, clip_stride, prm, tot_dev,
+                    logmel_dev, mfcc_dev, delta_dev, (cudaStream_t)stream);
+}
+
+int mmf_change_from_logmel(mmf_plan* plan, float* logmel_dev, const int32_t* clipmax_dev, int64_t n_clips, int64_t T,
+                           const mmf_change_params* prm, double* tot_dev, float* mfcc_dev, float* delta_dev,
+                           int32_t clamp_in_place, void* stream) {
+  if (!plan || !logmel_dev || !clipmax_dev || !prm || !tot_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_clips < 1 || T < 1) return fail(MMF_ERR_INVALID, "n_clips and T must be positive");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  const int rows = plan->cfg.n_mfcc - (prm->remove_first ? 1 : 0);
+  const size_t need = change_ws_bytes(plan, n_clips, T, false, mfcc_dev == nullptr, std::max(rows, 1));
+  int rc = ensure_ws(plan, need);
+  if (rc) return rc;
+  unsigned char* cur = (unsigned char*)plan->ws + (64 << 10);
+  return run_post(plan, cur, logmel_dev, clipmax_dev, n_clips, T, prm, tot_dev, mfcc_dev, delta_dev, clamp_in_place,
+                  (cudaStream_t)stream);
+}
+
+int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                      const mmf_change_params* prm, const mmf_modspec_params* mod, double* tot_host, float* mfcc_host,
+                      float* delta_host, float* mag_host, float* band_host) {
+  if (!plan || !pcm_host || !prm || !tot_host) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_clips < 1 || n_samples < 1) return fail(MMF_ERR_INVALID, "n_clips and n_samples must be positive");
+  if ((mag_host || band_host) && !mod) return fail(MMF_ERR_INVALID, "modulation outputs requested without parameters");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  const mmf_config& c = plan->cfg;
+  const int64_t T = mmf_num_frames(n_samples, c.n_fft, c.hop_length);
+  if (T < 1) return fail(MMF_ERR_INVALID, "input too short for one frame");
+  const int rows = std::max(1, c.n_mfcc - (prm->remove_first ? 1 : 0));
+  const bool want_mod = mod && (mag_host || band_host) && mod->win > 0;
+  int64_t n_win = 0;
+  int nbins = 0;
+  if (want_mod) {
+    if (mod->hop < 1 || mod->nfft < mod->win || mod->nfft > 4096 || (mod->nfft & (mod->nfft - 1)) || mod->n_bands < 0 ||
+        mod->n_bands > 16)
+      return fail(MMF_ERR_UNSUPPORTED, "bad modulation-spectrum parameters");
+    n_win = T >= mod->win ? 1 + (T - mod->win) / mod->hop : 0;
+    nbins = mod->nfft / 2 + 1;
+  }
+  const bool need_mfcc_dev = mfcc_host || want_mod;
+  // chunk the batch so that H2D of chunk i+1 overlaps compute of chunk i (two streams, two slots)
+  const size_t clip_bytes = (size_t)n_samples * 4;
+  int64_t chunk = std::max<int64_t>(1, (int64_t)((48u << 20) / clip_bytes));
+  chunk = std::min<int64_t>(chunk, n_clips);
+  const size_t pcm_slot = align_up((size_t)chunk * n_samples * 4, 256);
+  const size_t tot_slot = align_up((size_t)chunk * T * 8, 256);
+  const size_t mfcc_slot = need_mfcc_dev ? align_up((size_t)chunk * c.n_mfcc * T * 4, 256) : 0;
+  const size_t delta_slot = delta_host ? align_up((size_t)chunk * c.n_mfcc * T * 4, 256) : 0;
+  const size_t mag_slot = (want_mod && mag_host) ? align_up((size_t)chunk * c.n_mfcc * n_win * nbins * 4, 256) : 0;
+  const size_t band_slot = (want_mod && band_host) ? align_up((size_t)chunk * n_win * mod->n_bands * 4 + 4, 256) : 0;
+  const size_t change_slot = change_ws_bytes(plan, chunk, T, true, !need_mfcc_dev, rows);
+  const size_t slot = pcm_slot + tot_slot + mfcc_slot + delta_slot + mag_slot + band_slot + change_slot;
+  int rc = ensure_ws(plan, (64 << 10) + 2 * slot);
+  if (rc) return rc;
+  int *d_lo = nullptr, *d_hi = nullptr;
+  if (want_mod && band_host && mod->n_bands > 0) {
+    void *lo = nullptr, *hi = nullptr;
+    if ((rc = stage_consts(plan, mod->band_lo, (size_t)mod->n_bands * 4, 0, &lo, plan->streams[0]))) return rc;
+    if ((rc = stage_consts(plan, mod->band_hi, (size_t)mod->n_bands * 4, 256, &hi, plan->streams[0]))) return rc;
+    MMF_CUDA(cudaStreamSynchronize(plan->streams[0]));
+    d_lo = (int*)lo;
+    d_hi = (int*)hi;
+  }
+  int64_t done = 0;
+  for (int i = 0; done < n_clips; ++i, done += chunk) {
+    const int s = i & 1;
+    const int64_t nc = std::min<int64_t>(chunk, n_clips - done);
+    cudaStream_t st = plan->streams[s];
+    unsigned char* cur = (unsigned char*)plan->ws + (64 << 10) + (size_t)s * slot;
+    float* d_pcm = (float*)cur;
+    cur += pcm_slot;
+    double* d_tot = (double*)cur;
+    cur += tot_slot;
+    float* d_mfcc = need_mfcc_dev ? (float*)cur : nullptr;
+    cur += mfcc_slot;
+    float* d_delta = delta_host ? (float*)cur : nullptr;
+    cur += delta_slot;
+    float* d_mag = mag_slot ? (float*)cur : nullptr;
+    cur += mag_slot;
+    float* d_band = band_slot ? (float*)cur : nullptr;
+    cur += band_slot;
+    // stream order serialises reuse of slot s (chunk i-2 ran on the same stream)
+    if (clip_stride == n_samples) {
+      MMF_CUDA(cudaMemcpyAsync(d_pcm, pcm_host + (size_t)done * clip_stride, (size_t)nc * n_samples * 4,
+                               cudaMemcpyHostToDevice, st));
+    } else {
+      MMF_CUDA(cudaMemcpy2DAsync(d_pcm, (size_t)n_samples * 4, pcm_host + (size_t)done * clip_stride,
+                                 (size_t)clip_stride * 4, (size_t)n_samples * 4, (size_t)nc, cudaMemcpyHostToDevice,
+                                 st));
+    }
+    // run_change carves its own scratch after a 64 KB constants area
+    rc = run_change(plan, cur - (64 << 10), d_pcm, nc, n_samples, n_samples, prm, d_tot, nullptr, d_mfcc, d_delta, st);
+    if (rc) return rc;
+    if (want_mod && n_win > 0) {
+      cudaError_t e = modspec_launch(d_mfcc, nc, c.n_mfcc, T, mod->win, mod->hop, mod->nfft, d_mag, d_band, d_lo, d_hi,
+                                     mod->n_bands, st);
+      if (e != cudaSuccess) return cuda_fail(e, "modspec_kernel launch");
+    }
+    MMF_CUDA(cudaMemcpyAsync(tot_host + (size_t)done * T, d_tot, (size_t)nc * T * 8, cudaMemcpyDeviceToHost, st));
+    if (mfcc_host)
+      MMF_CUDA(cudaMemcpyAsync(mfcc_host + (size_t)done * c.n_mfcc * T, d_mfcc, (size_t)nc * c.n_mfcc * T * 4,
+                               cudaMemcpyDeviceToHost, st));
+    if (delta_host)
+      MMF_CUDA(cudaMemcpyAsync(delta_host + (size_t)done * c.n_mfcc * T, d_delta, (size_t)nc * c.n_mfcc * T * 4,
+                               cudaMemcpyDeviceToHost, st));
+    if (d_mag && n_win > 0)
+      MMF_CUDA(cudaMemcpyAsync(mag_host + (size_t)done * c.n_mfcc * n_win * nbins, d_mag,
+                               (size_t)nc * c.n_mfcc * n_win * nbins * 4, cudaMemcpyDeviceToHost, st));
+    if (d_band && n_win > 0)
+      MMF_CUDA(cudaMemcpyAsync(band_host + (size_t)done * n_win * mod->n_bands, d_band,
+                               (size_t)nc * n_win * mod->n_bands * 4, cudaMemcpyDeviceToHost, st));
+  }
+  MMF_CUDA(cudaStreamSynchronize(plan->streams[0]));
+  MMF_CUDA(cudaStreamSynchronize(plan->streams[1]));
+  return MMF_OK;
+}
+
+int mmf_mfcc_change_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, int64_t n_samples,
+                         int64_t clip_stride, const mmf_change_params* prm, double* tot_host, float* mfcc_host) {
+  return mmf_features_host(plan, pcm_host, n_clips, n_samples, clip_stride, prm, nullptr, tot_host, mfcc_host, nullptr,
+                           nullptr, nullptr);
+}
+
+}  // extern "C"

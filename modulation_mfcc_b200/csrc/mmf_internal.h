@@ -1,0 +1,127 @@
+// Internal declarations shared by the kernels and the C ABI (not installed).
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/mmf.h"
+
+namespace mmf {
+
+// ---- arguments of the fused STFT/mel kernel (passed by value)
+struct StftArgs {
+  const float* pcm;
+  long n_samples;
+  long clip_stride;
+  long n_tiles;
+  int tiles_per_clip;
+  int T;
+  int hop;
+  int TF;                // frames per tile (power of two, <= 32, multiple of frames/iteration)
+  int span_floats;       // (TF-1)*hop + n_fft + lead + 3 (start rounded down to 4 floats)
+  int span_alloc;        // span_floats rounded up to 256-float TMA boxes
+  int ppitch;            // power-tile row pitch (floats)
+  int pt_bufs;           // power-tile buffers (2 = double buffered, 1 = extra barrier per tile)
+  int lead;              // samples loaded ahead of the first frame (2 when pre-emphasis is on)
+  int use_tma;
+  int vec_ok;            // 64-bit shared loads allowed (hop even)
+  int split_regs;        // n_fft = 512: shuffle-based split step
+  int n_mels;
+  int bands_per_worker;
+  float amin;
+  float preemph;
+  const float* window;   // [n_fft]
+  const float2* tw1;     // [16*TPF]
+  const float2* tw2;     // [16*R3]
+  const int* seg_start;  // [n_mels + 2]
+  const float2* w2;      // [F] (falling, rising) mel weights per bin
+  float* logmel;         // [n_clips, n_mels, T] or null
+  int* clipmax;          // [n_clips] float keys or null
+  float* power;          // [n_clips, F, T] or null
+};
+
+struct StftGeometry {
+  int tpf, fpi, tw1, tw2, r3, m;
+};
+
+int stft_geometry(int n_fft, StftGeometry* g);
+size_t stft_smem_bytes(int n_fft, int span_alloc, int ppitch, int pt_bufs, int n_mels);
+cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
+                            cudaStream_t st);
+
+// ---- post-FFT kernels (post_kernels.cu)
+cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const int* clipmax, long n_clips, long T,
+                        int n_mels, int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place,
+                        cudaStream_t st);
+
+struct SosArgs {
+  int n_sections;
+  int padlen;
+  double sos[16][6];
+  double zi[16][2];
+};
+cudaError_t sosfiltfilt_launch(const void* x, int x_is_f32, long rows, long T, long xs, const SosArgs& a, double* y,
+                               long ys, cudaStream_t st);
+cudaError_t sosfiltfilt_launch_grouped(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
+                                       long group_stride, const SosArgs& a, double* y, long ys, cudaStream_t st);
+cudaError_t delta_norm_launch(const double* x, long n_clips, int rows, long T, int method, double* tot,
+                              cudaStream_t st);
+cudaError_t fir_filtfilt_launch(const double* x, long rows, long T, const double* b_dev, int n_taps, double* y,
+                                double* work, cudaStream_t st);
+cudaError_t stencil_launch(const double* x, long rows, long T, const double* coef_dev, int half, const double* el_dev,
+                           const double* er_dev, int n_edge, int n_edge_in, double* y, cudaStream_t st);
+cudaError_t modspec_launch(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, int nfft, float* mag,
+                           float* band, const int* band_lo_dev, const int* band_hi_dev, int n_bands, cudaStream_t st);
+cudaError_t rms_launch(const float* pcm, long n_clips, long n, long stride, int frame_length, int hop, int pad,
+                       long T, float* out, cudaStream_t st);
+cudaError_t fill_i32_launch(int* p, long n, int v, cudaStream_t st);
+
+// ---- host tables (host_tables.cpp)
+struct MelSparse {
+  std::vector<int> seg_start;  // n_mels + 2
+  std::vector<float> w2;       // 2*F (falling, rising)
+};
+void host_window(int win_length, int n_fft, std::vector<float>& w);
+void host_mel_dense(double sr, int n_fft, int n_mels, double fmin, double fmax, std::vector<float>& mel,
+                    std::vector<double>& mel_f);
+bool host_mel_sparse(const std::vector<float>& mel, const std::vector<double>& mel_f, double sr, int n_fft, int n_mels,
+                     MelSparse& out);
+void host_dct(int n_mfcc, int n_mels, std::vector<float>& d);
+void host_twiddles(int n_fft, const StftGeometry& g, std::vector<float2>& tw1, std::vector<float2>& tw2);
+int host_sos_zi(const double* sos, int n_sections, double* zi, int* padlen);
+
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+}  // namespace mmf
+
+struct mmf_plan {
+  mmf_config cfg;
+  int F;
+  int sm_count;
+  mmf::StftGeometry geo;
+  // tile geometry
+  int TF, ppitch, pt_bufs, ctas_per_sm, lead, bands_per_worker;
+  size_t smem;
+  // device constants
+  float* d_window = nullptr;
+  float2* d_tw1 = nullptr;
+  float2* d_tw2 = nullptr;
+  int* d_seg = nullptr;
+  float2* d_w2 = nullptr;
+  float* d_dct = nullptr;  // [n_mels][nc_pad]
+  int nc_pad = 0;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  // grow-only workspace for the composite entry points
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
+};

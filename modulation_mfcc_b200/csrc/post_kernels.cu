@@ -1,0 +1,495 @@
+// K3-K6 and the small filters around them: everything after the log-mel
+// spectrogram in get_MFCCS_change (script/mfcc.py:387-425) plus the helpers of
+// script/calc.py on the same path (get_velocity, RMS envelope).
+//
+// These stages move ~0.3 MB per clip against 0.64 MB of PCM for the fused STFT
+// kernel, so they are written for coalesced streaming access, not for math rate.
+#include <cfloat>
+#include <cstdint>
+
+#include "mmf_internal.h"
+
+namespace mmf {
+
+__device__ __forceinline__ float key_to_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
+// ---------------------------------------------------------------------------
+// K3: top_db clamp + DCT-II (+ delta).  One thread per frame; the DCT rows sit in
+// shared memory as [n_mels][NC] so each mel value feeds NC FMAs from broadcast
+// 128-bit shared loads.  Block = 128 frames with a one-frame halo on each side
+// when the delta (np.gradient) is requested.
+// ---------------------------------------------------------------------------
+constexpr int kMfccThreads = 128;
+
+template <int NC>
+__global__ void __launch_bounds__(kMfccThreads)
+    mfcc_kernel(const float* __restrict__ dct_pad, int dct_pitch, float* logmel, const int* __restrict__ clipmax, long T,
+                int n_mels, int n_mfcc, float top_db, float* __restrict__ mfcc, float* __restrict__ delta,
+                int clamp_in_place) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_dct = sm;                 // [n_mels][NC]
+  float* s_col = sm + n_mels * NC;   // [NC][kMfccThreads + 1]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_mels * NC; i += kMfccThreads) {
+    const int m = i / NC, j = i - m * NC;
+    s_dct[i] = dct_pad[m * dct_pitch + j];
+  }
+  __syncthreads();
+
+  const long clip = blockIdx.y;
+  const int halo = delta != nullptr ? 1 : 0;
+  const int per_block = kMfccThreads - 2 * halo;
+  const long t = (long)blockIdx.x * per_block - halo + tid;
+  const bool valid = t >= 0 && t < T;
+  const bool own = valid && tid >= halo && tid < kMfccThreads - halo;
+  const float thr = top_db >= 0.0f ? key_to_float(clipmax[clip]) - top_db : -FLT_MAX;
+
+  float acc[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) acc[j] = 0.0f;
+  if (valid) {
+    float* col = logmel + (size_t)clip * n_mels * T + t;
+    for (int m = 0; m < n_mels; ++m) {
+      float x = col[(size_t)m * T];
+      x = fmaxf(x, thr);
+      if (clamp_in_place && own) col[(size_t)m * T] = x;
+      const float4* d4 = reinterpret_cast<const float4*>(s_dct + m * NC);
+#pragma unroll
+      for (int j4 = 0; j4 < NC / 4; ++j4) {
+        const float4 d = d4[j4];
+        acc[4 * j4 + 0] = fmaf(d.x, x, acc[4 * j4 + 0]);
+        acc[4 * j4 + 1] = fmaf(d.y, x, acc[4 * j4 + 1]);
+        acc[4 * j4 + 2] = fmaf(d.z, x, acc[4 * j4 + 2]);
+        acc[4 * j4 + 3] = fmaf(d.w, x, acc[4 * j4 + 3]);
+      }
+    }
+  }
+  if (own) {
+    float* dst = mfcc + (size_t)clip * n_mfcc * T + t;
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (j < n_mfcc) dst[(size_t)j * T] = acc[j];
+  }
+  if (delta != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s_col[j * (kMfccThreads + 1) + tid] = acc[j];
+    __syncthreads();
+    if (own) {
+      float* dst = delta + (size_t)clip * n_mfcc * T + t;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        if (j < n_mfcc) {
+          const float* c = s_col + j * (kMfccThreads + 1) + tid;
+          float d;
+          if (T == 1) {
+            d = 0.0f;
+          } else if (t == 0) {
+            d = c[1] - c[0];
+          } else if (t == T - 1) {
+            d = c[0] - c[-1];
+          } else {
+            d = (c[1] - c[-1]) / 2.0f;
+          }
+          dst[(size_t)j * T] = d;
+        }
+      }
+    }
+  }
+}
+
+cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const int* clipmax, long n_clips, long T,
+                        int n_mels, int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place,
+                        cudaStream_t st) {
+  const int halo = delta != nullptr ? 1 : 0;
+  const int per_block = kMfccThreads - 2 * halo;
+  dim3 grid((unsigned)((T + per_block - 1) / per_block), (unsigned)n_clips);
+  int nc = n_mfcc <= 16 ? 16 : (n_mfcc <= 32 ? 32 : (n_mfcc <= 64 ? 64 : 128));
+  size_t smem = ((size_t)n_mels * nc + (size_t)nc * (kMfccThreads + 1)) * sizeof(float);
+#define MMF_MFCC_CASE(N)                                                                                         \
+  case N: {                                                                                                      \
+    cudaError_t e = cudaFuncSetAttribute(mfcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    if (e != cudaSuccess) return e;                                                                              \
+    mfcc_kernel<N><<<grid, kMfccThreads, smem, st>>>(dct_pad, nc_pad, logmel, clipmax, T, n_mels, n_mfcc, top_db, \
+                                                     mfcc, delta, clamp_in_place);                               \
+    break;                                                                                                       \
+  }
+  switch (nc) {
+    MMF_MFCC_CASE(16)
+    MMF_MFCC_CASE(32)
+    MMF_MFCC_CASE(64)
+    MMF_MFCC_CASE(128)
+  }
+#undef MMF_MFCC_CASE
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K4: scipy.signal.sosfiltfilt along time, one thread per row, float64.
+// Odd extension (padlen samples each side, computed in the input dtype as scipy
+// does), zi * first sample, forward cascade, same backwards, trim.  The forward
+// result of the T interior samples is parked in y and overwritten in place by
+// the backward pass; the right-hand extension lives in a per-thread tail.
+// ---------------------------------------------------------------------------
+constexpr int kMaxPad = 3 * (2 * 16 + 1);
+
+template <typename TIn, int NS>
+__global__ void __launch_bounds__(64)
+    sosfiltfilt_kernel(const TIn* __restrict__ x, long rows, long T, long x_row_stride, int group_rows,
+                       long group_stride, const SosArgs a, double* __restrict__ y, long y_row_stride) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const long g = r / group_rows, gi = r - g * group_rows;
+  const TIn* xr = x + g * group_stride + gi * x_row_stride;
+  double* yr = y + r * y_row_stride;
+  const int p = a.padlen;
+  const int ns = NS > 0 ? NS : a.n_sections;
+  constexpr int ZS = NS > 0 ? NS : 16;
+  double z0[ZS], z1[ZS];
+  double tail[kMaxPad];
+  const TIn x0 = xr[0], xl = xr[T - 1];
+  const TIn two = (TIn)2;
+
+  auto cascade = [&](double v) -> double {
+#pragma unroll
+    for (int s = 0; s < ZS; ++s) {
+      if (s < ns) {
+        const double out = fma(a.sos[s][0], v, z0[s]);
+        z0[s] = fma(a.sos[s][1], v, fma(-a.sos[s][4], out, z1[s]));
+        z1[s] = fma(a.sos[s][2], v, -a.sos[s][5] * out);
+        v = out;
+      }
+    }
+    return v;
+  };
+
+  // forward pass over [left ext | x | right ext]
+  const double e0 = (double)(TIn)(two * x0 - xr[p]);
+#pragma unroll
+  for (int s = 0; s < ZS; ++s)
+    if (s < ns) {
+      z0[s] = a.zi[s][0] * e0;
+      z1[s] = a.zi[s][1] * e0;
+    }
+  for (int i = 0; i < p; ++i) cascade((double)(TIn)(two * x0 - xr[p - i]));
+  for (long i = 0; i < T; ++i) yr[i] = cascade((double)xr[i]);
+  for (int j = 0; j < p; ++j) tail[j] = cascade((double)(TIn)(two * xl - xr[T - 2 - j]));
+
+  // backward pass
+  const double f0 = tail[p - 1];
+#pragma unroll
+  for (int s = 0; s < ZS; ++s)
+    if (s < ns) {
+      z0[s] = a.zi[s][0] * f0;
+      z1[s] = a.zi[s][1] * f0;
+    }
+  for (int j = p - 1; j >= 0; --j) cascade(tail[j]);
+  for (long i = T - 1; i >= 0; --i) yr[i] = cascade(yr[i]);
+}
+
+template <typename TIn>
+static cudaError_t sos_launch_t(const TIn* x, long rows, long T, long xs, int group_rows, long group_stride,
+                                const SosArgs& a, double* y, long ys, cudaStream_t st) {
+  const int threads = 64;
+  const unsigned grid = (unsigned)((rows + threads - 1) / threads);
+  switch (a.n_sections) {
+#define MMF_SOS_CASE(N)                                                                                          \
+  case N:                                                                                                        \
+    sosfiltfilt_kernel<TIn, N><<<grid, threads, 0, st>>>(x, rows, T, xs, group_rows, group_stride, a, y, ys);    \
+    break;
+    MMF_SOS_CASE(1)
+    MMF_SOS_CASE(2)
+    MMF_SOS_CASE(3)
+    MMF_SOS_CASE(4)
+    MMF_SOS_CASE(5)
+    MMF_SOS_CASE(6)
+    MMF_SOS_CASE(7)
+    MMF_SOS_CASE(8)
+#undef MMF_SOS_CASE
+    default:
+      sosfiltfilt_kernel<TIn, 0><<<grid, threads, 0, st>>>(x, rows, T, xs, group_rows, group_stride, a, y, ys);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t sosfiltfilt_launch_grouped(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
+                                       long group_stride, const SosArgs& a, double* y, long ys, cudaStream_t st) {
+  if (x_is_f32) return sos_launch_t<float>((const float*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+  return sos_launch_t<double>((const double*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+}
+
+cudaError_t sosfiltfilt_launch(const void* x, int x_is_f32, long rows, long T, long xs, const SosArgs& a, double* y,
+                               long ys, cudaStream_t st) {
+  // a single group: row r at x + r*xs
+  return sosfiltfilt_launch_grouped(x, x_is_f32, rows, T, xs, (int)(rows > 0x7fffffffL ? 0x7fffffff : rows), 0, a, y,
+                                    ys, st);
+}
+
+// ---------------------------------------------------------------------------
+// K5: derivative along time of the filtered MFCC rows and the norm over rows
+// (script/mfcc.py:405-415).  One thread per (clip, frame), coalesced along time.
+// ---------------------------------------------------------------------------
+__global__ void delta_norm_kernel(const double* __restrict__ x, int rows, long T, int method,
+                                  double* __restrict__ tot) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const long clip = blockIdx.y;
+  const double* base = x + (size_t)clip * rows * T;
+  double s = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    const double* f = base + (size_t)r * T;
+    double d;
+    if (T == 1) {
+      d = 0.0;
+    } else if (t == 0) {
+      d = (method == 0 || T < 3) ? f[1] - f[0] : (-3.0 * f[0] + 4.0 * f[1] - f[2]) / 2.0;
+    } else if (t == T - 1) {
+      d = (method == 0 || T < 3) ? f[T - 1] - f[T - 2] : (3.0 * f[T - 1] - 4.0 * f[T - 2] + f[T - 3]) / 2.0;
+    } else {
+      d = (f[t + 1] - f[t - 1]) / 2.0;
+    }
+    s += d * d;
+  }
+  tot[(size_t)clip * T + t] = sqrt(s) / (double)rows;
+}
+
+cudaError_t delta_norm_launch(const double* x, long n_clips, int rows, long T, int method, double* tot,
+                              cudaStream_t st) {
+  dim3 grid((unsigned)((T + 255) / 256), (unsigned)n_clips);
+  delta_norm_kernel<<<grid, 256, 0, st>>>(x, rows, T, method, tot);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// scipy.signal.filtfilt(b, 1, x): zero-phase FIR.  With a == 1 the lfilter
+// initial state zi*x[0] is "the past was constantly x[0]", so each pass is a
+// plain convolution over the odd-extended signal with a constant extension
+// beyond its first sample -- no recurrence, one thread per output.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double odd_ext_at(const double* xr, long T, int p, long i) {
+  if (i < p) return 2.0 * xr[0] - xr[p - i];
+  if (i < p + T) return xr[i - p];
+  return 2.0 * xr[T - 1] - xr[T - 2 - (i - p - T)];
+}
+
+__global__ void fir_fwd_kernel(const double* __restrict__ x, long T, int p, const double* __restrict__ b, int n_taps,
+                               double* __restrict__ work) {
+  const long L = T + 2L * p;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const double* xr = x + (size_t)blockIdx.y * T;
+  double acc = 0.0;
+  for (int j = n_taps - 1; j >= 0; --j) {
+    const long m = i - j;
+    acc = fma(b[j], odd_ext_at(xr, T, p, m < 0 ? 0 : m), acc);
+  }
+  work[(size_t)blockIdx.y * L + i] = acc;
+}
+
+__global__ void fir_bwd_kernel(const double* __restrict__ work, long T, int p, const double* __restrict__ b,
+                               int n_taps, double* __restrict__ y) {
+  const long L = T + 2L * p;
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= T) return;
+  const double* w = work + (size_t)blockIdx.y * L;
+  const long i = n + p;
+  double acc = 0.0;
+  for (int j = n_taps - 1; j >= 0; --j) {
+    const long m = i + j;
+    acc = fma(b[j], w[m >= L ? L - 1 : m], acc);
+  }
+  y[(size_t)blockIdx.y * T + n] = acc;
+}
+
+cudaError_t fir_filtfilt_launch(const double* x, long rows, long T, const double* b_dev, int n_taps, double* y,
+                                double* work, cudaStream_t st) {
+  const int p = 3 * n_taps;
+  const long L = T + 2L * p;
+  dim3 g1((unsigned)((L + 255) / 256), (unsigned)rows), g2((unsigned)((T + 255) / 256), (unsigned)rows);
+  fir_fwd_kernel<<<g1, 256, 0, st>>>(x, T, p, b_dev, n_taps, work);
+  fir_bwd_kernel<<<g2, 256, 0, st>>>(work, T, p, b_dev, n_taps, y);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Banded stencil with dense boundary rows (np.gradient / savgol 'interp' /
+// findiff; script/calc.py:635-645, script/mfcc.py:130).
+// ---------------------------------------------------------------------------
+__global__ void stencil_kernel(const double* __restrict__ x, long T, const double* __restrict__ coef, int half,
+                               const double* __restrict__ el, const double* __restrict__ er, int n_edge,
+                               int n_edge_in, double* __restrict__ y) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const double* xr = x + (size_t)blockIdx.y * T;
+  double acc = 0.0;
+  if (t < n_edge) {
+    for (int i = 0; i < n_edge_in; ++i) acc = fma(el[t * n_edge_in + i], xr[i], acc);
+  } else if (t >= T - n_edge) {
+    const long q = t - (T - n_edge);
+    for (int i = 0; i < n_edge_in; ++i) acc = fma(er[q * n_edge_in + i], xr[T - n_edge_in + i], acc);
+  } else {
+    for (int o = -half; o <= half; ++o) acc = fma(coef[o + half], xr[t + o], acc);
+  }
+  y[(size_t)blockIdx.y * T + t] = acc;
+}
+
+cudaError_t stencil_launch(const double* x, long rows, long T, const double* coef_dev, int half, const double* el_dev,
+                           const double* er_dev, int n_edge, int n_edge_in, double* y, cudaStream_t st) {
+  dim3 grid((unsigned)((T + 255) / 256), (unsigned)rows);
+  stencil_kernel<<<grid, 256, 0, st>>>(x, T, coef_dev, half, el_dev, er_dev, n_edge, n_edge_in, y);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K6: modulation spectrum of the MFCC trajectories.
+// One CTA per (window, clip); each warp transforms one coefficient's window at a
+// time: mean removal (shuffle reduction), periodic Hann, zero padding, radix-2
+// FFT in shared memory (float64 arithmetic: magnitudes reach 1e3 and the parity
+// budget is 1e-3 absolute), |X| out, and per-band energies reduced with warp
+// shuffles into shared accumulators shared by the coefficients.
+// ---------------------------------------------------------------------------
+constexpr int kModWarps = 4;
+constexpr int kMaxBands = 16;
+
+__global__ void __launch_bounds__(kModWarps * 32)
+    modspec_kernel(const float* __restrict__ mfcc, int n_coef, long T, int win, int hop, int nfft, int log2n,
+                   long n_win, float* __restrict__ mag, float* __restrict__ band, const int* __restrict__ band_lo,
+                   const int* __restrict__ band_hi, int n_bands) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  double2* s_tw = reinterpret_cast<double2*>(sm_raw);           // [nfft/2]
+  double2* s_buf = s_tw + nfft / 2;                             // [kModWarps][nfft]
+  double* s_hann = reinterpret_cast<double*>(s_buf + kModWarps * nfft);  // [win]
+  __shared__ double s_band[kMaxBands];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long j = blockIdx.x;   // window
+  const long clip = blockIdx.y;
+  const int nb = nfft / 2 + 1;
+
+  for (int i = tid; i < nfft / 2; i += blockDim.x) {
+    double s, c;
+    sincospi(-2.0 * (double)i / (double)nfft, &s, &c);
+    s_tw[i] = make_double2(c, s);
+  }
+  for (int i = tid; i < win; i += blockDim.x) s_hann[i] = 0.5 - 0.5 * cospi(2.0 * (double)i / (double)win);
+  if (tid < kMaxBands) s_band[tid] = 0.0;
+  __syncthreads();
+
+  double2* buf = s_buf + warp * nfft;
+  for (int c = warp; c < n_coef; c += kModWarps) {
+    const float* src = mfcc + ((size_t)clip * n_coef + c) * T + j * hop;
+    double sum = 0.0;
+    for (int i = lane; i < win; i += 32) sum += (double)src[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double mean = sum / (double)win;
+    for (int i = lane; i < nfft; i += 32) {
+      const double v = i < win ? ((double)src[i] - mean) * s_hann[i] : 0.0;
+      buf[__brev((unsigned)i) >> (32 - log2n)] = make_double2(v, 0.0);
+    }
+    __syncwarp();
+    for (int s = 0; s < log2n; ++s) {
+      const int half = 1 << s;
+      const int tw_step = nfft >> (s + 1);
+      for (int bfly = lane; bfly < nfft / 2; bfly += 32) {
+        const int pos = bfly & (half - 1);
+        const int i0 = ((bfly >> s) << (s + 1)) + pos, i1 = i0 + half;
+        const double2 w = s_tw[pos * tw_step];
+        const double2 u = buf[i0], v = buf[i1];
+        const double2 tv = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+        buf[i0] = make_double2(u.x + tv.x, u.y + tv.y);
+        buf[i1] = make_double2(u.x - tv.x, u.y - tv.y);
+      }
+      __syncwarp();
+    }
+    float* mdst = mag != nullptr ? mag + (((size_t)clip * n_coef + c) * n_win + j) * nb : nullptr;
+    for (int k = lane; k < nb; k += 32) {
+      const double2 X = buf[k];
+      const double p = X.x * X.x + X.y * X.y;
+      if (mdst) mdst[k] = (float)sqrt(p);
+    }
+    if (band != nullptr) {
+      for (int b = 0; b < n_bands; ++b) {
+        double e = 0.0;
+        for (int k = band_lo[b] + lane; k < band_hi[b]; k += 32) {
+          const double2 X = buf[k];
+          e += X.x * X.x + X.y * X.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if (lane == 0) atomicAdd(&s_band[b], e);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (band != nullptr && tid < n_bands) band[((size_t)clip * n_win + j) * n_bands + tid] = (float)s_band[tid];
+}
+
+cudaError_t modspec_launch(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, int nfft, float* mag,
+                           float* band, const int* band_lo_dev, const int* band_hi_dev, int n_bands, cudaStream_t st) {
+  int log2n = 0;
+  while ((1 << log2n) < nfft) ++log2n;
+  const long n_win = T >= win ? 1 + (T - win) / hop : 0;
+  if (n_win <= 0) return cudaSuccess;
+  size_t smem = (size_t)(nfft / 2) * 16 + (size_t)kModWarps * nfft * 16 + (size_t)win * 8;
+  cudaError_t e = cudaFuncSetAttribute(modspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) return e;
+  // grid.y is limited to 65535: fold clips beyond that into several launches
+  for (long c0 = 0; c0 < n_clips; c0 += 65535) {
+    const long nc = n_clips - c0 < 65535 ? n_clips - c0 : 65535;
+    dim3 grid((unsigned)n_win, (unsigned)nc);
+    modspec_kernel<<<grid, kModWarps * 32, smem, st>>>(
+        mfcc + (size_t)c0 * n_coef * T, n_coef, T, win, hop, nfft, log2n, n_win,
+        mag ? mag + (size_t)c0 * n_coef * n_win * (nfft / 2 + 1) : nullptr,
+        band ? band + (size_t)c0 * n_win * n_bands : nullptr, band_lo_dev, band_hi_dev, n_bands);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// RMS envelope (librosa.feature.rms; script/calc.py:326-331): one warp per frame.
+// ---------------------------------------------------------------------------
+__global__ void rms_kernel(const float* __restrict__ pcm, long n, long stride, int frame_length, int hop, int pad,
+                           long T, float* __restrict__ out) {
+  const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= T) return;
+  const long clip = blockIdx.y;
+  const float* x = pcm + (size_t)clip * stride;
+  const long start = w * hop - pad;
+  float s = 0.0f;
+  for (int i = lane; i < frame_length; i += 32) {
+    const long m = start + i;
+    const float v = (m >= 0 && m < n) ? x[m] : 0.0f;
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[(size_t)clip * T + w] = sqrtf(s / (float)frame_length);
+}
+
+cudaError_t rms_launch(const float* pcm, long n_clips, long n, long stride, int frame_length, int hop, int pad, long T,
+                       float* out, cudaStream_t st) {
+  const int threads = 256;  // 8 frames per block
+  dim3 grid((unsigned)((T + 7) / 8), (unsigned)n_clips);
+  rms_kernel<<<grid, threads, 0, st>>>(pcm, n, stride, frame_length, hop, pad, T, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void fill_i32_kernel(int* p, long n, int v) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+cudaError_t fill_i32_launch(int* p, long n, int v, cudaStream_t st) {
+  fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace mmf

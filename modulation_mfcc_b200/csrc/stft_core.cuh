@@ -73,6 +73,27 @@ MMF_HD void ph_load(float2 (&v)[16], const float* span, int frame_off, int tau, 
   }
 }
 
+// Same with first-order pre-emphasis y'[n] = y[n] - a*y[n-1] applied to the
+// un-padded signal (y[-1] = 0) before the zero centre padding: n_valid is the
+// number of samples from the frame start to the end of the clip, so samples at
+// or beyond it stay exactly zero.  Needs one sample of history before the frame
+// (the span is loaded with lead >= 1).
+template <int NFFT>
+MMF_HD void ph_load_pre(float2 (&v)[16], const float* span, int frame_off, int tau, const float2 (&wreg)[16], float a,
+                        long n_valid) {
+  using C = FftCfg<NFFT>;
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int i0 = 2 * (tau + C::TPF * n2);
+    const float xm = span[frame_off + i0 - 1];
+    const float x0 = span[frame_off + i0];
+    const float x1 = span[frame_off + i0 + 1];
+    const float y0 = (i0 < n_valid) ? x0 - a * xm : 0.0f;
+    const float y1 = (i0 + 1 < n_valid) ? x1 - a * x0 : 0.0f;
+    v[n2] = make_float2(y0 * wreg[n2].x, y1 * wreg[n2].y);
+  }
+}
+
 // ---- pass 1: 16-point DFT over n2 and the W_M^{n1*k2} twiddle
 template <int NFFT>
 MMF_HD void ph_pass1(float2 (&v)[16], const float2* tw1, int tau) {

@@ -1,0 +1,337 @@
+// K1+K2: fused frame -> (pre-emphasis) -> Hann window -> real FFT -> |X|^2 ->
+// Slaney mel projection -> 10*log10 -> per-clip max, for a batch of clips.
+//
+// Replaces the librosa chain invoked at script/mfcc.py:387 (stft, abs**2,
+// filters.mel + einsum, power_to_db before the top_db clamp).
+//
+// Execution model (sm_100a):
+//  * persistent CTAs (2 per SM, 256 threads), each looping over tiles of TF
+//    consecutive frames of one clip;
+//  * the PCM span of a tile ((TF-1)*hop + n_fft samples, hop windows overlap) is
+//    brought in once by TMA (cp.async.bulk.tensor, 1 KB boxes, double buffered,
+//    mbarrier completion); out-of-range coordinates are zero-filled by the TMA
+//    unit, which *is* librosa's center=True / pad_mode='constant' padding, so no
+//    padded copy of the audio ever exists;
+//  * FFT data lives in registers (16 complex points per thread), Hann window in
+//    registers, one shared-memory exchange between radix-16 passes, and for
+//    n_fft = 512 the real-FFT split step pairs bins with warp shuffles;
+//  * the power tile stays in shared memory and is projected on the (sparse,
+//    two-slopes-per-bin) mel filterbank by all warps, log'd and streamed out
+//    with coalesced stores; the 1 MB/clip power spectrum never touches HBM
+//    unless the caller asks for it (mmf_stft_power).
+#include <cfloat>
+#include <cstdint>
+
+#include "mmf_internal.h"
+#include "stft_core.cuh"
+
+namespace mmf {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MMF_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MMF_DONE_%=;\n"
+      "bra MMF_WAIT_%=;\n"
+      "MMF_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// monotone float -> int key so that atomicMax(int) orders like float compare
+__device__ __forceinline__ int float_key(float f) {
+  int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7FFFFFFF;
+}
+
+template <int TPF>
+__device__ __forceinline__ void frame_sync() {
+  if constexpr (TPF <= 32) {
+    __syncwarp();
+  } else {
+    __syncthreads();
+  }
+}
+
+constexpr int kThreads = 256;
+constexpr int kBox = 256;  // floats per TMA box (1 KB)
+
+// One thread queues the TMA boxes of a tile's PCM span.  Negative and
+// past-the-end sample coordinates are zero-filled by the TMA unit.
+template <int NFFT>
+__device__ __forceinline__ void issue_span(const CUtensorMap* tmap, const StftArgs& p, long tile, float* dst,
+                                           uint64_t* bar) {
+  const int clip = (int)(tile / p.tiles_per_clip);
+  const int t0 = (int)(tile % p.tiles_per_clip) * p.TF;
+  // TMA box start addresses must be 16-byte aligned: round the first sample down
+  // to a multiple of 4 floats; the kernel adds the remainder to its frame offsets
+  const int g0 = (t0 * p.hop - NFFT / 2 - p.lead) & ~3;
+  // order earlier generic-proxy accesses of this buffer before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(bar, (uint32_t)p.span_alloc * 4u);
+  for (int bx = 0; bx < p.span_alloc / kBox; ++bx) tma_load_2d(dst + bx * kBox, tmap, g0 + bx * kBox, clip, bar);
+}
+
+template <int NFFT>
+__global__ void __launch_bounds__(kThreads, 2)
+    stft_mel_kernel(const __grid_constant__ CUtensorMap tmap, const StftArgs p) {
+  using C = FftCfg<NFFT>;
+  constexpr int FPI = kThreads / C::TPF;  // frames transformed per iteration
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+
+  // ---- shared memory carve-up (mirrors stft_smem_bytes() on the host)
+  float* s_span = reinterpret_cast<float*>(smem_raw);                       // [2][span_alloc]
+  float* s_ptile = s_span + 2 * p.span_alloc;                               // [pt_bufs][F*ppitch]
+  float2* s_xb = reinterpret_cast<float2*>(s_ptile + ((p.pt_bufs * C::F * p.ppitch + 3) & ~3));  // [FPI][XBUF]
+  float2* s_tw1 = s_xb + FPI * C::XBUF;                                     // [TW1]
+  float2* s_tw2 = s_tw1 + C::TW1;                                           // [TW2]
+  float2* s_w2 = s_tw2 + C::TW2;                                            // [F]
+  int* s_seg = reinterpret_cast<int*>(s_w2 + C::F);                         // [n_mels + 2]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_seg + ((p.n_mels + 2 + 1) & ~1));  // [2]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int tau = tid % C::TPF;
+  const int slot = tid / C::TPF;
+
+  for (int i = tid; i < C::TW1; i += kThreads) s_tw1[i] = p.tw1[i];
+  for (int i = tid; i < C::TW2; i += kThreads) s_tw2[i] = p.tw2[i];
+  for (int i = tid; i < C::F; i += kThreads) s_w2[i] = p.w2[i];
+  for (int i = tid; i < p.n_mels + 2; i += kThreads) s_seg[i] = p.seg_start[i];
+
+  // Hann window of this thread's 16 complex points, pre-scaled by the 1/2 of the split step
+  float2 wreg[16];
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int c = tau + C::TPF * n2;
+    const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * c);
+    wreg[n2] = make_float2(0.5f * w.x, 0.5f * w.y);
+  }
+  float2 wtau;
+  sincospif(-2.0f * (float)tau / (float)NFFT, &wtau.y, &wtau.x);
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int lead = p.lead;  // samples loaded ahead of the first frame (pre-emphasis history)
+  const long n_tiles = p.n_tiles;
+
+  long tile = blockIdx.x;
+  if (p.use_tma && tid == 0 && tile < n_tiles) issue_span<NFFT>(&tmap, p, tile, s_span, &s_bar[0]);
+
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int clip = (int)(tile / p.tiles_per_clip);
+    const int t0 = (int)(tile % p.tiles_per_clip) * p.TF;
+    float* span = s_span + (size_t)b * p.span_alloc;
+    // the span starts at the 16-byte aligned sample at or below the first needed one
+    const int g_first = t0 * p.hop - NFFT / 2 - lead;
+    const int shift = g_first - (g_first & ~3);
+    float* ptile = s_ptile + (size_t)(p.pt_bufs == 2 ? b : 0) * C::F * p.ppitch;
+
+    if (p.use_tma) {
+      // prefetch the next tile into the other buffer: its last readers finished
+      // before the __syncthreads that closed the previous tile's FFT phase
+      if (tid == 0 && tile + gridDim.x < n_tiles)
+        issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span + (size_t)(b ^ 1) * p.span_alloc, &s_bar[b ^ 1]);
+      mbar_wait(&s_bar[b], (uint32_t)(it >> 1) & 1u);
+    } else {
+      // plain coalesced loader (clip stride or base not 16-byte aligned)
+      const long g0 = (long)(g_first & ~3);
+      const float* src = p.pcm + (size_t)clip * p.clip_stride;
+      for (int i = tid; i < p.span_floats; i += kThreads) {
+        const long n = g0 + i;
+        span[i] = (n >= 0 && n < p.n_samples) ? __ldg(src + n) : 0.0f;
+      }
+      __syncthreads();
+    }
+
+    // ---------------- FFT phase: FPI frames per iteration ----------------
+    float2* xb = s_xb + slot * C::XBUF;
+    for (int fi = 0; fi < p.TF / FPI; ++fi) {
+      const int f = fi * FPI + slot;
+      const int off = shift + lead + f * p.hop;
+      float2 v[16];
+      if (p.preemph != 0.0f) {
+        // samples from this frame's start to the end of the clip (frame start = f*hop - n_fft/2)
+        const long n_valid = p.n_samples - ((long)(t0 + f) * p.hop - NFFT / 2);
+        ph_load_pre<NFFT>(v, span, off, tau, wreg, p.preemph, n_valid);
+      } else if (p.vec_ok && !(shift & 1)) {
+        ph_load<NFFT, true>(v, span, off, tau, wreg);
+      } else {
+        ph_load<NFFT, false>(v, span, off, tau, wreg);
+      }
+      ph_pass1<NFFT>(v, s_tw1, tau);
+      frame_sync<C::TPF>();  // previous iteration's readers of xb are done
+      ph_x1_write<NFFT>(v, xb, tau);
+      frame_sync<C::TPF>();
+      ph_x1_read<NFFT>(v, xb, tau);
+      ph_pass2<NFFT>(v, s_tw2, tau);
+      if constexpr (C::R3 > 1) {
+        frame_sync<C::TPF>();
+        ph_x2_write<NFFT>(v, xb, tau);
+        frame_sync<C::TPF>();
+        ph_x2_read<NFFT>(v, xb, tau);
+        ph_pass3<NFFT>(v);
+      }
+      bool done = false;
+      if constexpr (NFFT == 512) {
+        if (p.split_regs) {
+          // partner lane holds Z[M-k]: lane (16 - s) & 15 of the same half-warp, register 15 - r
+          const int src = ((16 - tau) & 15) | (lane & 16);
+          float2 bpart[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float bx = __shfl_sync(0xffffffffu, v[15 - r].x, src);
+            const float by = __shfl_sync(0xffffffffu, v[15 - r].y, src);
+            const float2 own = v[(16 - r) & 15];
+            bpart[r] = (tau == 0) ? own : make_float2(bx, by);
+          }
+          ph_split_regs512(v, bpart, ptile, p.ppitch, f, tau, wtau);
+          done = true;
+        }
+      }
+      if (!done) {
+        frame_sync<C::TPF>();
+        ph_z_write<NFFT>(v, xb, tau);
+        frame_sync<C::TPF>();
+        ph_split_smem<NFFT>(xb, ptile, p.ppitch, f, tau, wtau);
+      }
+    }
+    __syncthreads();  // power tile complete; span[b] no longer needed
+
+    const int t_valid = min(p.TF, p.T - t0);
+    if (p.power != nullptr) {
+      float* dst = p.power + (size_t)clip * C::F * p.T + t0;
+      for (int e = tid; e < C::F * p.TF; e += kThreads) {
+        const int k = e / p.TF, t = e - k * p.TF;
+        if (t < t_valid) dst[(size_t)k * p.T + t] = ptile[k * p.ppitch + t];
+      }
+    }
+    if (p.logmel != nullptr) {
+      // ---------------- mel phase: lane -> (frame, band group) ----------------
+      const int t = lane % p.TF;
+      const int worker = (tid >> 5) * (32 / p.TF) + lane / p.TF;
+      const int m0 = worker * p.bands_per_worker;
+      const int m1 = min(p.n_mels, m0 + p.bands_per_worker);
+      float mx = -FLT_MAX;
+      if (m0 < p.n_mels && t < t_valid) {
+        float* dst = p.logmel + (size_t)clip * p.n_mels * p.T + t0 + t;
+        const float amin = p.amin;
+        mel_column(ptile, p.ppitch, t, s_seg, s_w2, m0, m1, [&](int m, float val) {
+          const float db = 10.0f * log10f(fmaxf(amin, val));
+          dst[(size_t)m * p.T] = db;
+          mx = fmaxf(mx, db);
+        });
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0 && mx > -FLT_MAX) atomicMax(p.clipmax + clip, float_key(mx));
+    }
+    // with two power-tile buffers no barrier is needed here: the next tile writes
+    // the other buffer and the tile after that is separated by the next tile's
+    // __syncthreads; with one buffer the readers must drain first
+    if (p.pt_bufs == 1) __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+
+template <int NFFT>
+static size_t smem_bytes_t(int span_alloc, int ppitch, int pt_bufs, int n_mels) {
+  using C = FftCfg<NFFT>;
+  constexpr int FPI = kThreads / C::TPF;
+  size_t b = 0;
+  b += (size_t)2 * span_alloc * 4;
+  b += (size_t)((pt_bufs * C::F * ppitch + 3) & ~3) * 4;
+  b += (size_t)FPI * C::XBUF * 8;
+  b += (size_t)(C::TW1 + C::TW2 + C::F) * 8;
+  b += (size_t)((n_mels + 2 + 1) & ~1) * 4;
+  b += 16;
+  return b;
+}
+
+template <int NFFT>
+static void geometry_t(StftGeometry* g) {
+  using C = FftCfg<NFFT>;
+  g->tpf = C::TPF;
+  g->fpi = kThreads / C::TPF;
+  g->tw1 = C::TW1;
+  g->tw2 = C::TW2;
+  g->r3 = C::R3;
+  g->m = C::M;
+}
+
+int stft_geometry(int n_fft, StftGeometry* g) {
+  switch (n_fft) {
+    case 256: geometry_t<256>(g); return 0;
+    case 512: geometry_t<512>(g); return 0;
+    case 1024: geometry_t<1024>(g); return 0;
+    case 2048: geometry_t<2048>(g); return 0;
+    case 4096: geometry_t<4096>(g); return 0;
+    default: return -1;
+  }
+}
+
+size_t stft_smem_bytes(int n_fft, int span_alloc, int ppitch, int pt_bufs, int n_mels) {
+  switch (n_fft) {
+    case 256: return smem_bytes_t<256>(span_alloc, ppitch, pt_bufs, n_mels);
+    case 512: return smem_bytes_t<512>(span_alloc, ppitch, pt_bufs, n_mels);
+    case 1024: return smem_bytes_t<1024>(span_alloc, ppitch, pt_bufs, n_mels);
+    case 2048: return smem_bytes_t<2048>(span_alloc, ppitch, pt_bufs, n_mels);
+    case 4096: return smem_bytes_t<4096>(span_alloc, ppitch, pt_bufs, n_mels);
+    default: return 0;
+  }
+}
+
+template <int NFFT>
+static cudaError_t launch_t(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(stft_mel_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  stft_mel_kernel<NFFT><<<grid, kThreads, smem, st>>>(tmap, a);
+  return cudaGetLastError();
+}
+
+cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
+                            cudaStream_t st) {
+  switch (n_fft) {
+    case 256: return launch_t<256>(tmap, a, grid, smem, st);
+    case 512: return launch_t<512>(tmap, a, grid, smem, st);
+    case 1024: return launch_t<1024>(tmap, a, grid, smem, st);
+    case 2048: return launch_t<2048>(tmap, a, grid, smem, st);
+    case 4096: return launch_t<4096>(tmap, a, grid, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace mmf

@@ -1,0 +1,375 @@
+"""GPU parity tests: every CUDA entry point, called through the C ABI, against the
+CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8d):
+  * log-mel: relative error of the linear mel power <= 1e-4 for bins above the
+    amin floor (== 4.3e-4 dB absolute);
+  * MFCC, delta, modulation magnitudes, totChange: <= 1e-3 absolute;
+  * time anchors T: exact.
+"""
+
+import numpy as np
+import pytest
+import scipy.signal
+
+import oracle
+import modulation_mfcc_b200 as mm
+from modulation_mfcc_b200 import _lib
+from modulation_mfcc_b200.synth import synth_batch, synth_clip
+
+pytestmark = pytest.mark.gpu
+
+LOGMEL_REL = 1e-4  # on linear mel power
+ABS_TOL = 1e-3
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+CONFIGS = {
+    # name: (sr, n_fft, winLen, tStep, n_mels, n_mfcc, fmin, fmax, seconds)
+    "cfg1_16k": (16000, 512, 0.025, 0.01, 40, 13, 0.0, 8000.0, 10.0),
+    "gui_default": (10000, 512, 0.025, 0.005, 128, 13, 100.0, 10000.0, 4.0),
+    "cfg3_44k": (44100, 2048, 0.025, 0.01, 128, 20, 0.0, 22050.0, 3.0),
+    "n1024": (22050, 1024, 0.04, 0.0125, 64, 16, 50.0, 11025.0, 2.0),
+    "n256": (8000, 256, 0.025, 0.01, 32, 12, 0.0, 4000.0, 2.0),
+    "n4096": (48000, 4096, 0.08, 0.02, 96, 24, 20.0, 24000.0, 2.0),
+}
+
+
+def _cfg(name, **over):
+    sr, n_fft, winLen, tStep, n_mels, n_mfcc, fmin, fmax, secs = CONFIGS[name]
+    win, hop = mm.frame_sizes(sr, winLen, tStep)
+    cfg = mm.MfccConfig(sr, n_fft, win, hop, n_mels, n_mfcc, fmin, fmax, **over)
+    return cfg, secs
+
+
+def _mel_rel_err(logmel_gpu, logmel_ref_unclamped):
+    """Relative error in linear mel power for bins above the amin floor."""
+    ok = logmel_ref_unclamped > -99.0
+    d = np.abs(logmel_gpu - logmel_ref_unclamped)[ok]
+    return float(np.max(np.abs(10.0 ** (d / 10.0) - 1.0))) if d.size else 0.0
+
+
+def _oracle_unclamped(y, cfg):
+    M, inter = oracle.mfcc(
+        y, cfg.sample_rate, n_mfcc=cfg.n_mfcc, win_length=cfg.win_length, hop_length=cfg.hop_length, n_fft=cfg.n_fft,
+        fmin=cfg.fmin, fmax=cfg.fmax, n_mels=cfg.n_mels, return_intermediates=True)
+    unclamped = oracle.power_to_db(inter["melspec"], top_db=None)
+    return M, inter, unclamped
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("flags", [0, _lib.MMF_FLAG_NO_TMA])
+def test_stft_power(name, flags, cuda_device):
+    cfg, secs = _cfg(name, flags=flags)
+    y = synth_batch(0, 3, int(cfg.sample_rate * secs) + 37, cfg.sample_rate)
+    plan = mm.get_plan(cfg)
+    P = plan.stft_power(y).cpu().numpy()
+    for i in range(y.shape[0]):
+        ref = oracle.stft_power(y[i], cfg.n_fft, cfg.hop_length, cfg.win_length)
+        assert P[i].shape == ref.shape
+        # fp32 FFT: error relative to the frame's spectral peak
+        peak = ref.max(axis=0, keepdims=True)
+        assert np.max(np.abs(P[i] - ref) / peak) < 2e-6, name
+
+
+def test_stft_power_split_variants_agree(cuda_device):
+    cfg, secs = _cfg("cfg1_16k")
+    y = synth_batch(5, 2, 16000 * 2, 16000)
+    a = mm.get_plan(cfg).stft_power(y).cpu().numpy()
+    b = mm.get_plan(mm.plan.replace(cfg, flags=_lib.MMF_FLAG_SPLIT_SMEM)).stft_power(y).cpu().numpy()
+    assert np.array_equal(a, b)  # same arithmetic, different data path
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_logmel_mfcc_delta(name, cuda_device):
+    cfg, secs = _cfg(name)
+    y = synth_batch(10, 2, int(cfg.sample_rate * secs), cfg.sample_rate)
+    plan = mm.get_plan(cfg)
+    lm, cmax = plan.logmel(y)
+    lm_unclamped = lm.cpu().numpy().copy()
+    mf, dl = plan.mfcc(lm, cmax, delta=True, clamp_in_place=True)
+    lm_c, mf, dl = lm.cpu().numpy(), mf.cpu().numpy(), dl.cpu().numpy()
+    for i in range(y.shape[0]):
+        M, inter, unclamped = _oracle_unclamped(y[i], cfg)
+        assert _mel_rel_err(lm_unclamped[i], unclamped) < LOGMEL_REL, name
+        assert np.max(np.abs(lm_c[i] - inter["logmel"])) < 4.4e-4, name  # clamped log-mel, dB
+        assert np.max(np.abs(mf[i] - M)) < ABS_TOL, name
+        assert np.max(np.abs(dl[i] - np.gradient(M, axis=1))) < ABS_TOL, name
+
+
+def test_clamp_is_active_on_gui_default(cuda_device):
+    """fmax above Nyquist leaves empty mel filters at -100 dB, so top_db=80 always clamps."""
+    cfg, secs = _cfg("gui_default")
+    y = synth_clip(3, int(cfg.sample_rate * secs), cfg.sample_rate)
+    plan = mm.get_plan(cfg)
+    lm, cmax = plan.logmel(y)
+    raw = lm.cpu().numpy()[0].copy()
+    plan.mfcc(lm, cmax, clamp_in_place=True)
+    clamped = lm.cpu().numpy()[0]
+    assert raw.min() == pytest.approx(-100.0)
+    assert clamped.min() == pytest.approx(raw.max() - 80.0, abs=1e-4)
+    assert (clamped > raw).any()
+
+
+def test_edge_clips(cuda_device):
+    cfg, _ = _cfg("cfg1_16k")
+    n = 16000
+    plan = mm.get_plan(cfg)
+    clips = np.zeros((5, n), np.float32)
+    clips[1] = 0.25                                   # DC
+    t = np.arange(n) / 16000.0
+    clips[2] = 0.5 * np.sin(2 * np.pi * (16000 / 512 * 20) * t)  # tone on bin 20
+    clips[3, 0] = 1.0                                 # impulse at the first sample
+    clips[4, -1] = 1.0                                # impulse at the last sample
+    lm, cmax = plan.logmel(clips)
+    raw = lm.cpu().numpy().copy()
+    mf = plan.mfcc(lm, cmax).cpu().numpy()
+    P = plan.stft_power(clips).cpu().numpy()
+    assert np.all(raw[0] == -100.0)                   # all-zero clip: amin floor, no clamp effect
+    assert np.argmax(P[2][:, 50]) == 20
+    for i in range(5):
+        M, inter, unclamped = _oracle_unclamped(clips[i], cfg)
+        ref_p = inter["power"]
+        assert np.max(np.abs(P[i] - ref_p)) <= 2e-6 * max(ref_p.max(), 1e-30)
+        # impulses make most mel bins tiny but non-zero: compare in dB with an absolute bound
+        assert np.max(np.abs(mf[i] - M)) < ABS_TOL
+
+
+@pytest.mark.parametrize("x_dtype", ["f32", "f64"])
+@pytest.mark.parametrize("order,wn", [(6, 0.24), (6, 0.12), (2, 0.3), (4, 0.048)])
+def test_sosfiltfilt(order, wn, x_dtype, cuda_device):
+    torch = _torch()
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((5, 12, 333)).cumsum(axis=-1)
+    if x_dtype == "f32":
+        x = x.astype(np.float32)
+    sos = scipy.signal.butter(order, wn, output="sos")
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    y = plan.sosfiltfilt(torch.as_tensor(x).cuda(), sos).cpu().numpy()
+    ref = scipy.signal.sosfiltfilt(sos, x)
+    assert y.dtype == np.float64
+    assert np.max(np.abs(y - ref)) < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_sosfiltfilt_bandpass_and_too_short(cuda_device):
+    torch = _torch()
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((3, 400))
+    sos = scipy.signal.butter(4, [0.1, 0.3], btype="bandpass", output="sos")
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    y = plan.sosfiltfilt(torch.as_tensor(x).cuda(), sos).cpu().numpy()
+    assert np.max(np.abs(y - scipy.signal.sosfiltfilt(sos, x))) < 1e-9
+    sos6 = scipy.signal.butter(6, 0.24, output="sos")
+    ok = plan.sosfiltfilt(torch.as_tensor(x[:, :22]).cuda(), sos6).cpu().numpy()  # T = 22: shortest legal
+    assert np.max(np.abs(ok - scipy.signal.sosfiltfilt(sos6, x[:, :22]))) < 1e-9
+    with pytest.raises(mm.MmfError) as ei:
+        plan.sosfiltfilt(torch.as_tensor(x[:, :21]).cuda(), sos6)
+    assert ei.value.code == _lib.MMF_ERR_TOO_SHORT
+    assert "greater than padlen, which is 21" in ei.value.msg
+
+
+KW_GUI = dict(channelN=0, tStep=0.005, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=100, maxFreq=10000, removeFirst=1,
+              filtCutoff=12, filtOrd=6, diffMethod="grad", outFilter="iir", outFiltType="low", outFiltCutOff=[12],
+              outFiltLen=6, outFiltPolyOrd=3)
+
+
+def test_get_MFCCS_change_gui_call(cuda_device):
+    """The exact call of script/main.py:750-769."""
+    y = synth_clip(1, 40000, 10000)
+    tot, T = mm.get_MFCCS_change(y, 10000, **KW_GUI)
+    ref, Tref = oracle.get_MFCCS_change(y, 10000, **KW_GUI)
+    assert tot.dtype == np.float64 and T.dtype == np.float64
+    assert np.array_equal(T, Tref)
+    assert np.max(np.abs(tot - ref)) < ABS_TOL
+
+
+@pytest.mark.parametrize(
+    "over",
+    [
+        dict(outFilter=None),
+        dict(diffMethod="sg"),
+        dict(removeFirst=0),
+        dict(outFilter="fir", outFiltLen=11, outFiltCutOff=[12]),
+        dict(outFilter="sg", outFiltLen=7, outFiltPolyOrd=3, outFiltCutOff=[12]),
+        dict(outFilter="iir", outFiltType="band", outFiltCutOff=[2, 20], outFiltLen=4),
+        dict(outFilter="iir", outFiltType="high", outFiltCutOff=[5], outFiltLen=3),
+        dict(tStep=0.01, n_fft=1024, winLen=0.04),
+    ],
+)
+def test_get_MFCCS_change_variants(over, cuda_device):
+    y = synth_clip(2, 30000, 10000)
+    kw = dict(KW_GUI)
+    kw.update(over)
+    tot, T = mm.get_MFCCS_change(y, 10000, **kw)
+    ref, Tref = oracle.get_MFCCS_change(y, 10000, **kw)
+    assert np.array_equal(T, Tref)
+    assert np.max(np.abs(tot - ref)) < ABS_TOL, over
+
+
+def test_get_MFCCS_change_multichannel_and_features(cuda_device):
+    y2 = np.stack([synth_clip(3, 20000, 10000), synth_clip(4, 20000, 10000)])
+    kw = dict(KW_GUI)
+    kw["channelN"] = 1
+    tot, T, feats = mm.get_MFCCS_change(y2, 10000, return_features=True, **kw)
+    ref, Tref, rf = oracle.get_MFCCS_change(y2, 10000, return_features=True, **kw)
+    assert np.max(np.abs(tot - ref)) < ABS_TOL
+    assert np.max(np.abs(feats["mfcc"] - rf["mfcc"])) < ABS_TOL
+    assert np.max(np.abs(feats["logmel"] - rf["logmel"])) < 4.4e-4
+
+
+def test_get_MFCCS_change_errors(cuda_device):
+    y = synth_clip(2, 30000, 10000)
+    kw = dict(KW_GUI)
+    with pytest.raises(TypeError):  # signature default outFiltCutOff=[None] (script/mfcc.py:308, :93)
+        mm.get_MFCCS_change(y, 10000, **{**kw, "outFiltCutOff": [None]})
+    with pytest.raises(Exception, match="Cut off frequencies must be smaller"):
+        mm.get_MFCCS_change(y, 10000, **{**kw, "outFiltCutOff": [200]})
+    with pytest.raises(Exception, match="filtType must be one among"):
+        mm.get_MFCCS_change(y, 10000, **{**kw, "outFiltType": "notch"})
+    with pytest.raises(ValueError, match="greater than padlen"):  # 21 frames
+        mm.get_MFCCS_change(y[: 50 * 20], 10000, **kw)
+    with pytest.raises(ValueError):  # win_length > n_fft
+        mm.get_MFCCS_change(y, 10000, **{**kw, "winLen": 0.1})
+
+
+def test_batch_equals_single_and_host_call(cuda_device):
+    """Batched clips give bit-identical results to one-at-a-time calls, through both
+    the device API and the host-buffer C entry point."""
+    sr = 16000
+    y = synth_batch(20, 9, sr * 2, sr)
+    kw = dict(tStep=0.01, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=0, maxFreq=8000, outFiltCutOff=[12], n_mels=40)
+    tot_b, T = mm.get_MFCCS_change_batch(y, sr, **kw)
+    for i in (0, 4, 8):
+        tot_1, _ = mm.get_MFCCS_change(y[i], sr, **kw)
+        assert np.array_equal(tot_b[i], tot_1)
+        ref, Tref = oracle.get_MFCCS_change(y[i], sr, **kw)
+        assert np.max(np.abs(tot_b[i] - ref)) < ABS_TOL
+        assert np.array_equal(T, Tref)
+    torch = _torch()
+    tot_d, _ = mm.get_MFCCS_change_batch(torch.as_tensor(y).cuda(), sr, **kw)
+    assert np.array_equal(tot_d.cpu().numpy(), tot_b)
+
+
+def test_feature_bundle_and_modspec(cuda_device):
+    sr = 16000
+    y = synth_batch(30, 3, sr * 10, sr)
+    res = mm.mfcc_features_batch(y, sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
+    for i in range(3):
+        ref = oracle.mfcc_features(y[i], sr)
+        assert np.max(np.abs(res["mfcc"][i] - ref["mfcc"])) < ABS_TOL
+        assert np.max(np.abs(res["delta"][i] - ref["delta"])) < ABS_TOL
+        assert np.max(np.abs(res["logmel"][i] - ref["logmel"])) < 4.4e-4
+        assert np.max(np.abs(res["totChange"][i] - ref["totChange"])) < ABS_TOL
+        assert res["modspec"][i].shape == ref["modspec"].shape == (13, 19, 65)
+        # modulation magnitudes inherit the MFCC's fp32 error times the window sum (<= 50)
+        assert np.max(np.abs(res["modspec"][i] - ref["modspec"])) < 5e-3
+        assert np.allclose(res["band_energy"][i], ref["band_energy"], rtol=1e-4, atol=1e-3)
+        assert np.array_equal(res["T"], ref["T"])
+
+
+def test_modspec_kernel_alone(cuda_device):
+    """The trajectory FFT itself, on identical float32 input: <= 1e-3 absolute."""
+    torch = _torch()
+    rng = np.random.default_rng(11)
+    M = (rng.standard_normal((4, 13, 1001)).cumsum(axis=-1) * 0.5).astype(np.float32)
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    for (win_s, hop_s, fr) in [(1.0, 0.5, 100.0), (1.0, 0.01, 100.0), (2.0, 0.5, 200.0), (10.01, 1.0, 100.0)]:
+        Lw, Hw, nfft, n_win = mm.modspec_sizes(1001, fr, win_s, hop_s)
+        bins = mm.band_bins(nfft, fr)
+        mag, band = plan.modspec(torch.as_tensor(M).cuda(), Lw, Hw, nfft, bins)
+        mag, band = mag.cpu().numpy(), band.cpu().numpy()
+        for i in range(4):
+            rm, rb, _ = oracle.modulation_spectrum(M[i], fr, mod_win_s=win_s, mod_hop_s=hop_s)
+            assert mag[i].shape == rm.shape
+            assert np.max(np.abs(mag[i] - rm)) < ABS_TOL
+            assert np.allclose(band[i], rb, rtol=2e-6, atol=1e-6)
+
+
+def test_get_velocity_and_filters(cuda_device):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(777).cumsum()
+    for kw in [dict(method="gradient", difference=1), dict(method="gradient", difference=2),
+               dict(method="sg", difference=1, width=5, polyOrder=2), dict(method="sg", difference=2, width=7, polyOrder=3),
+               dict(method="finDiff", difference=1, accOrder=2), dict(method="finDiff", difference=2, accOrder=2),
+               dict(method="finDiff", difference=1, accOrder=4)]:
+        for sr in (1.0, 200.0):
+            got = mm.get_velocity(x, sr, **kw)
+            ref = oracle.get_velocity(x, sr, **kw)
+            assert got.dtype == np.float64
+            assert np.max(np.abs(got - ref)) <= 1e-9 * max(1.0, np.abs(ref).max()), kw
+    with pytest.raises(ValueError, match="Méthode inconnue"):
+        mm.get_velocity(x, 1.0, method="nope")
+    for kw in [dict(filt="iir", cutOff=[12], filtLen=6), dict(filt="fir", cutOff=[12], filtLen=21),
+               dict(filt="fir", cutOff=[5, 30], filtLen=31, filtType="band"), dict(filt="sg", cutOff=[12], filtLen=9, polyOrd=3),
+               dict(filt="iir", cutOff=[20], filtLen=4, filtType="high")]:
+        got = mm.applyFilter(x, 200.0, **kw)
+        ref = oracle.applyFilter(x, 200.0, **kw)
+        assert np.max(np.abs(got - ref)) < 1e-9 * max(1.0, np.abs(ref).max()), kw
+    assert mm.applyFilter(x, 200.0, filt="unknown", cutOff=[12]) is None
+
+
+def test_rms_envelope(cuda_device):
+    sr = 16000
+    y = synth_clip(6, sr * 3, sr)
+    amp, t = mm.calculate_amplitude_envelope(y, sr)
+    ramp, rt = oracle.calculate_amplitude_envelope(y, sr)
+    assert amp.dtype == np.float32 and amp.shape == ramp.shape
+    assert np.array_equal(t, rt)
+    assert np.allclose(amp, ramp, rtol=1e-4, atol=1e-7)
+    # raw int16 PCM, as script/main.py:843-849 passes it
+    yi = (y * 32767).astype(np.int16)
+    amp, _ = mm.calculate_amplitude_envelope(yi, sr, winLen=0.05, hopLen=0.005, center=False, outFilter="iir", outFiltCutOff=[12])
+    ramp, _ = oracle.calculate_amplitude_envelope(yi.astype(np.float32), sr, winLen=0.05, hopLen=0.005, center=False, outFilter="iir", outFiltCutOff=[12])
+    assert np.allclose(amp, ramp, rtol=1e-4, atol=1e-3)
+
+
+def test_preemphasis_extension(cuda_device):
+    cfg, _ = _cfg("cfg1_16k", preemph=0.97)
+    y = synth_clip(8, 16000, 16000)
+    yp = y.copy()
+    yp[1:] = y[1:] - np.float32(0.97) * y[:-1]
+    P = mm.get_plan(cfg).stft_power(y).cpu().numpy()[0]
+    ref = oracle.stft_power(yp, cfg.n_fft, cfg.hop_length, cfg.win_length)
+    assert np.max(np.abs(P - ref) / ref.max(axis=0, keepdims=True)) < 2e-6
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE cfg 2 at full size (1024 x 10 s): size-independent properties."""
+    torch = _torch()
+    sr, n = 16000, 160000
+    pcm = mm.synth_batch_device(1024, n, sr, seed=1234, device=cuda_device)
+    fx = mm.FeatureExtractor(sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
+    res = fx(pcm)
+    assert res["mfcc"].shape == (1024, 13, 1001) and res["modspec"].shape == (1024, 13, 19, 65)
+    for v in res.values():
+        assert bool(torch.isfinite(v).all())
+    # (1) host-recomputed parity sample
+    idx = [0, 511, 1023]
+    host = pcm[idx].cpu().numpy()
+    for j, i in enumerate(idx):
+        ref = oracle.mfcc_features(host[j], sr)
+        assert np.max(np.abs(res["mfcc"][i].cpu().numpy() - ref["mfcc"])) < ABS_TOL
+        assert np.max(np.abs(res["totChange"][i].cpu().numpy() - ref["totChange"])) < ABS_TOL
+    # (2) batch position independence: the same clip anywhere in the batch gives identical bits
+    perm = torch.randperm(1024, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(1))
+    res_p = fx(pcm[perm].contiguous())
+    assert torch.equal(res_p["mfcc"], res["mfcc"][perm])
+    assert torch.equal(res_p["totChange"], res["totChange"][perm])
+    # (3) gain linearity: x2 amplitude -> +20*log10(2) dB on every unclamped log-mel bin, c0 shifts, c1.. unchanged
+    plan = fx.plan
+    lm1, _ = plan.logmel(pcm[:64])
+    lm2, _ = plan.logmel(pcm[:64] * 0.5)
+    assert float((lm1 - lm2 - 20 * np.log10(2.0)).abs().max()) < 2e-4
+    # (4) Parseval on the power spectrum: sum_k c_k |X_k|^2 == n_fft * sum_n (w x)^2
+    P = plan.stft_power(pcm[:8])
+    w = torch.as_tensor(oracle.padded_hann(400, 512), device=cuda_device)
+    xp = torch.nn.functional.pad(pcm[:8].double(), (256, 256))
+    fr = xp.unfold(1, 512, 160) * w
+    lhs = 2 * P.double().sum(dim=1) - P[:, 0].double() - P[:, -1].double()
+    rhs = 512 * (fr**2).sum(dim=-1)
+    assert float(((lhs - rhs).abs() / rhs).max()) < 1e-5
