@@ -223,7 +223,7 @@ def run_b200(args):
         if record:
             e1.record()
             k1_events.append((e0, e1))
-        res = plan.change_from_logmel(lm, cmax, prm)  # clamp+DCT+delta, IIR, derivative+norm, IIR
+        res = plan.change_from_logmel(lm, cmax, prm, clamp_in_place=False)  # clamp+DCT+delta, IIR, derivative+norm, IIR
         mag, band = plan.modspec(res["mfcc"], Lw, Hw, nfft, bins)
         if world > 1:  # the only collective: final gather of the per-clip feature
             dist.all_gather_into_tensor(gathered, res["totChange"])

@@ -192,6 +192,10 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
 int mmf_mfcc_change_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, int64_t n_samples,
                          int64_t clip_stride, const mmf_change_params* prm, double* tot_host, float* mfcc_host);
 
+/* sizeof() of the ABI structs as this library was compiled (0: mmf_config,
+ * 1: mmf_change_params, 2: mmf_modspec_params) so bindings can verify their layout. */
+int mmf_abi_sizeof(int32_t which);
+
 /* Number of kernels this library has launched on the calling thread since the
  * last reset (bench.py reports it as gpu_launches). */
 int64_t mmf_launch_count(int32_t reset);

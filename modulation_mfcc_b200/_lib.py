@@ -17,7 +17,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmmf_b200.so"
-SOURCES = ["stft_mel.cu", "post_kernels.cu", "c_api.cu", "host_tables.cpp"]
+SOURCES = ["stft_mel.cu", "post_kernels.cu", "modspec_fast.cu", "c_api.cu", "host_tables.cpp"]
 HEADERS = ["fft_regs.cuh", "stft_core.cuh", "mmf_internal.h", "../../include/mmf.h"]
 
 NVCC_FLAGS = [
@@ -156,6 +156,7 @@ _SIGNATURES = {
         C.c_int,
         [_vp, _vp, _i64, _i64, _i64, C.POINTER(mmf_change_params), C.POINTER(mmf_modspec_params), _vp, _vp, _vp, _vp, _vp],
     ),
+    "mmf_abi_sizeof": (C.c_int, [_i32]),
     "mmf_launch_count": (_i64, [_i32]),
 }
 

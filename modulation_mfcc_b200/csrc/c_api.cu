@@ -93,11 +93,84 @@ static int fill_sos(const double* sos, int n_sections, SosArgs* a) {
 
 }  // namespace mmf
 
+
+namespace mmf {
+
+// Tables of the trajectory FFT live in the plan and are rebuilt only when the
+// window / FFT size / band edges change.
+static int ensure_mod_tables(mmf_plan* p, int win, int nfft, const int* lo, const int* hi, int n_bands) {
+  bool same = p->mod_win == win && p->mod_nfft == nfft && p->mod_n_bands == n_bands;
+  for (int b = 0; same && b < n_bands; ++b) same = p->mod_lo[b] == lo[b] && p->mod_hi[b] == hi[b];
+  if (same) return MMF_OK;
+  MMF_CUDA(cudaDeviceSynchronize());
+  cudaFree(p->d_mod_hann);
+  cudaFree(p->d_mod_tw1);
+  cudaFree(p->d_mod_tw2);
+  cudaFree(p->d_mod_lo);
+  cudaFree(p->d_mod_hi);
+  p->d_mod_hann = nullptr;
+  p->d_mod_tw1 = p->d_mod_tw2 = nullptr;
+  p->d_mod_lo = p->d_mod_hi = nullptr;
+  p->mod_n_bands = -1;
+  std::vector<float> hann(nfft, 0.0f);
+  for (int i = 0; i < win; ++i) hann[i] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * (double)i / (double)win));
+  StftGeometry g;
+  modspec_geometry(nfft, &g);
+  std::vector<float2> tw1, tw2;
+  if (modspec_fast_supported(nfft)) host_twiddles(nfft, g, tw1, tw2);
+  std::vector<int> vlo(16, 0), vhi(16, 0);
+  for (int b = 0; b < n_bands; ++b) {
+    vlo[b] = lo[b];
+    vhi[b] = hi[b];
+  }
+  cudaError_t e;
+  if ((e = upload(&p->d_mod_hann, hann)) != cudaSuccess || (e = upload(&p->d_mod_tw1, tw1)) != cudaSuccess ||
+      (e = upload(&p->d_mod_tw2, tw2)) != cudaSuccess || (e = upload(&p->d_mod_lo, vlo)) != cudaSuccess ||
+      (e = upload(&p->d_mod_hi, vhi)) != cudaSuccess)
+    return cuda_fail(e, "uploading modulation-spectrum tables");
+  p->mod_win = win;
+  p->mod_nfft = nfft;
+  p->mod_n_bands = n_bands;
+  for (int b = 0; b < 16; ++b) {
+    p->mod_lo[b] = vlo[b];
+    p->mod_hi[b] = vhi[b];
+  }
+  return MMF_OK;
+}
+
+static int run_modspec(mmf_plan* p, const float* mfcc, int64_t n_clips, int n_coef, int64_t T, int win, int hop,
+                       int nfft, float* mag, float* band, const int* lo, const int* hi, int n_bands, cudaStream_t st) {
+  if (T < win) return MMF_OK;
+  if (!band) n_bands = 0;
+  int rc = ensure_mod_tables(p, win, nfft, lo, hi, n_bands);
+  if (rc) return rc;
+  cudaError_t e;
+  if (modspec_fast_supported(nfft)) {
+    e = modspec_fast_launch(mfcc, n_clips, n_coef, T, win, hop, nfft, p->d_mod_hann, p->d_mod_tw1, p->d_mod_tw2, mag,
+                            n_bands > 0 ? band : nullptr, p->d_mod_lo, p->d_mod_hi, n_bands, p->sm_count, st);
+  } else {
+    e = modspec_launch(mfcc, n_clips, n_coef, T, win, hop, nfft, mag, n_bands > 0 ? band : nullptr, p->d_mod_lo,
+                       p->d_mod_hi, n_bands, st);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "modspec kernel launch");
+  return MMF_OK;
+}
+
+}  // namespace mmf
+
 using namespace mmf;
 
 extern "C" {
 
 int mmf_version(void) { return MMF_VERSION; }
+int mmf_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return (int)sizeof(mmf_config);
+    case 1: return (int)sizeof(mmf_change_params);
+    case 2: return (int)sizeof(mmf_modspec_params);
+    default: return -1;
+  }
+}
 const char* mmf_last_error(void) { return g_err.c_str(); }
 int64_t mmf_launch_count(int32_t reset) {
   const long v = g_launches;
@@ -266,6 +339,11 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_w2);
   cudaFree(p->d_dct);
   cudaFree(p->ws);
+  cudaFree(p->d_mod_hann);
+  cudaFree(p->d_mod_tw1);
+  cudaFree(p->d_mod_tw2);
+  cudaFree(p->d_mod_lo);
+  cudaFree(p->d_mod_hi);
   if (p->pinned) cudaFreeHost(p->pinned);
   for (int i = 0; i < 2; ++i)
     if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
@@ -480,26 +558,18 @@ int mmf_modspec(mmf_plan* plan, const float* mfcc_dev, int64_t n_clips, int32_t 
                 int32_t hop, int32_t nfft, float* mag_dev, float* band_dev, const int32_t* band_lo_host,
                 const int32_t* band_hi_host, int32_t n_bands, void* stream) {
   if (!plan || !mfcc_dev) return fail(MMF_ERR_INVALID, "NULL argument");
-  if (win < 1 || hop < 1 || nfft < win || nfft < 2 || nfft > 4096 || (nfft & (nfft - 1)))
-    return fail(MMF_ERR_UNSUPPORTED, "need 1 <= win <= nfft, nfft a power of two <= 4096, hop >= 1");
+  if (win < 1 || hop < 1 || nfft < win || nfft < 32 || nfft > 4096 || (nfft & (nfft - 1)))
+    return fail(MMF_ERR_UNSUPPORTED, "need 1 <= win <= nfft, nfft a power of two in [32, 4096], hop >= 1");
   if (n_bands < 0 || n_bands > 16) return fail(MMF_ERR_UNSUPPORTED, "n_bands must be in [0, 16]");
   if (band_dev && n_bands > 0 && (!band_lo_host || !band_hi_host)) return fail(MMF_ERR_INVALID, "band edges are NULL");
+  if (n_clips < 1 || n_coef < 1) return fail(MMF_ERR_INVALID, "n_clips and n_coef must be positive");
   MMF_CUDA(cudaSetDevice(plan->cfg.device));
-  cudaStream_t st = (cudaStream_t)stream;
-  void *lo = nullptr, *hi = nullptr;
-  if (band_dev && n_bands > 0) {
+  if (band_dev)
     for (int b = 0; b < n_bands; ++b)
       if (band_lo_host[b] < 0 || band_hi_host[b] > nfft / 2 + 1 || band_lo_host[b] > band_hi_host[b])
         return fail(MMF_ERR_INVALID, "band bin range outside [0, nfft/2+1]");
-    int rc = stage_consts(plan, band_lo_host, (size_t)n_bands * 4, 0, &lo, st);
-    if (rc) return rc;
-    if ((rc = stage_consts(plan, band_hi_host, (size_t)n_bands * 4, 256, &hi, st))) return rc;
-  }
-  cudaError_t e = modspec_launch(mfcc_dev, n_clips, n_coef, T, win, hop, nfft, mag_dev,
-                                 (band_dev && n_bands > 0) ? band_dev : nullptr, (const int*)lo, (const int*)hi,
-                                 n_bands, st);
-  if (e != cudaSuccess) return cuda_fail(e, "modspec_kernel launch");
-  return MMF_OK;
+  return run_modspec(plan, mfcc_dev, n_clips, n_coef, T, win, hop, nfft, mag_dev, band_dev, band_lo_host, band_hi_host,
+                     n_bands, (cudaStream_t)stream);
 }
 
 int mmf_rms(mmf_plan* plan, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
@@ -657,15 +727,6 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
   const size_t slot = pcm_slot + tot_slot + mfcc_slot + delta_slot + mag_slot + band_slot + change_slot;
   int rc = ensure_ws(plan, (64 << 10) + 2 * slot);
   if (rc) return rc;
-  int *d_lo = nullptr, *d_hi = nullptr;
-  if (want_mod && band_host && mod->n_bands > 0) {
-    void *lo = nullptr, *hi = nullptr;
-    if ((rc = stage_consts(plan, mod->band_lo, (size_t)mod->n_bands * 4, 0, &lo, plan->streams[0]))) return rc;
-    if ((rc = stage_consts(plan, mod->band_hi, (size_t)mod->n_bands * 4, 256, &hi, plan->streams[0]))) return rc;
-    MMF_CUDA(cudaStreamSynchronize(plan->streams[0]));
-    d_lo = (int*)lo;
-    d_hi = (int*)hi;
-  }
   int64_t done = 0;
   for (int i = 0; done < n_clips; ++i, done += chunk) {
     const int s = i & 1;
@@ -697,9 +758,9 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
     rc = run_change(plan, cur - (64 << 10), d_pcm, nc, n_samples, n_samples, prm, d_tot, nullptr, d_mfcc, d_delta, st);
     if (rc) return rc;
     if (want_mod && n_win > 0) {
-      cudaError_t e = modspec_launch(d_mfcc, nc, c.n_mfcc, T, mod->win, mod->hop, mod->nfft, d_mag, d_band, d_lo, d_hi,
-                                     mod->n_bands, st);
-      if (e != cudaSuccess) return cuda_fail(e, "modspec_kernel launch");
+      if ((rc = run_modspec(plan, d_mfcc, nc, c.n_mfcc, T, mod->win, mod->hop, mod->nfft, d_mag, d_band, mod->band_lo,
+                            mod->band_hi, mod->n_bands, st)))
+        return rc;
     }
     MMF_CUDA(cudaMemcpyAsync(tot_host + (size_t)done * T, d_tot, (size_t)nc * T * 8, cudaMemcpyDeviceToHost, st));
     if (mfcc_host)

@@ -77,6 +77,11 @@ cudaError_t stencil_launch(const double* x, long rows, long T, const double* coe
                            const double* er_dev, int n_edge, int n_edge_in, double* y, cudaStream_t st);
 cudaError_t modspec_launch(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, int nfft, float* mag,
                            float* band, const int* band_lo_dev, const int* band_hi_dev, int n_bands, cudaStream_t st);
+bool modspec_fast_supported(int nfft);
+void modspec_geometry(int nfft, StftGeometry* g);
+cudaError_t modspec_fast_launch(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, int nfft,
+                                const float* hann, const float2* tw1, const float2* tw2, float* mag, float* band,
+                                const int* lo, const int* hi, int n_bands, int sm_count, cudaStream_t st);
 cudaError_t rms_launch(const float* pcm, long n_clips, long n, long stride, int frame_length, int hop, int pad,
                        long T, float* out, cudaStream_t st);
 cudaError_t fill_i32_launch(int* p, long n, int v, cudaStream_t st);
@@ -117,6 +122,14 @@ struct mmf_plan {
   float* d_dct = nullptr;  // [n_mels][nc_pad]
   int nc_pad = 0;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  // tables of the trajectory FFT, rebuilt when (win, nfft, bands) change
+  int mod_win = 0, mod_nfft = 0, mod_n_bands = -1;
+  int mod_lo[16] = {0}, mod_hi[16] = {0};
+  float* d_mod_hann = nullptr;
+  float2* d_mod_tw1 = nullptr;
+  float2* d_mod_tw2 = nullptr;
+  int* d_mod_lo = nullptr;
+  int* d_mod_hi = nullptr;
   // grow-only workspace for the composite entry points
   void* ws = nullptr;
   size_t ws_bytes = 0;

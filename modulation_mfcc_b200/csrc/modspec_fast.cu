@@ -1,0 +1,198 @@
+// K6 (fast path): modulation spectrum of the MFCC trajectories with the same
+// register-resident mixed-radix FFT as the STFT kernel.
+//
+// One "slot" of TPF = nfft/32 threads transforms one (clip, coefficient, window)
+// trajectory window: 32 real samples per thread straight from global memory
+// (the MFCC tensor is small and L2 resident), mean removal with a shuffle
+// reduction over the slot, periodic Hann, zero padding to nfft, real FFT
+// (16 x R2 x R3 passes, shared-memory exchange), |X| out, and the per-band
+// energies reduced over the warp with shuffles (all slots of a warp belong to the
+// same (clip, window) pair) followed by one atomicAdd per warp and band.
+#include <cfloat>
+
+#include "mmf_internal.h"
+#include "stft_core.cuh"
+
+namespace mmf {
+
+constexpr int kModThreads = 256;
+
+template <int NFFT>
+__global__ void __launch_bounds__(kModThreads)
+    modspec_fast_kernel(const float* __restrict__ mfcc, int n_coef, long T, int win, int hop, long n_win, long n_pairs,
+                        int cpad, const float* __restrict__ hann, const float2* __restrict__ g_tw1,
+                        const float2* __restrict__ g_tw2, float* __restrict__ mag, float* __restrict__ band,
+                        const int* __restrict__ band_lo, const int* __restrict__ band_hi, int n_bands) {
+  using C = FftCfg<NFFT>;
+  static_assert(C::TPF <= 32, "one slot must fit in a warp");
+  constexpr int SLOTS = kModThreads / C::TPF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_xb = reinterpret_cast<float2*>(smem_raw);  // [SLOTS][XBUF]
+  float2* s_tw1 = s_xb + SLOTS * C::XBUF;              // [TW1]
+  float2* s_tw2 = s_tw1 + C::TW1;                      // [TW2]
+  __shared__ int s_blo[16], s_bhi[16];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int tau = tid % C::TPF, slot_in_block = tid / C::TPF;
+  for (int i = tid; i < C::TW1; i += kModThreads) s_tw1[i] = g_tw1[i];
+  for (int i = tid; i < C::TW2; i += kModThreads) s_tw2[i] = g_tw2[i];
+  if (tid < 16) {
+    s_blo[tid] = tid < n_bands ? band_lo[tid] : 0;
+    s_bhi[tid] = tid < n_bands ? band_hi[tid] : 0;
+  }
+  float2 wreg[16];
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int c = tau + C::TPF * n2;
+    wreg[n2] = make_float2(0.5f * hann[2 * c], 0.5f * hann[2 * c + 1]);  // zero beyond win
+  }
+  float2 wtau;
+  sincospif(-2.0f * (float)tau / (float)NFFT, &wtau.y, &wtau.x);
+  __syncthreads();
+
+  float2* xb = s_xb + slot_in_block * C::XBUF;
+  const int nb = NFFT / 2 + 1;
+  const float inv_win = 1.0f / (float)win;
+  const long n_slots = n_pairs * cpad;
+  // round the trip count up so every thread of the block runs the same number of
+  // iterations (the exchanges synchronise whole warps)
+  const long stride = (long)gridDim.x * SLOTS;
+  for (long base = (long)blockIdx.x * SLOTS; base < n_slots; base += stride) {
+    const long slot = base + slot_in_block;
+    const long pair = slot / cpad;
+    const int coef = (int)(slot - pair * cpad);
+    const bool valid = slot < n_slots && coef < n_coef;
+    const long clip = pair / n_win, j = pair - clip * n_win;
+    const float* src = mfcc + ((size_t)clip * n_coef + coef) * T + j * hop;
+    float2 v[16];
+    float sum = 0.0f;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const int i0 = 2 * (tau + C::TPF * n2);
+      float x0 = 0.0f, x1 = 0.0f;
+      if (valid) {
+        if (i0 < win) x0 = __ldg(src + i0);
+        if (i0 + 1 < win) x1 = __ldg(src + i0 + 1);
+      }
+      v[n2] = make_float2(x0, x1);
+      sum += x0 + x1;
+    }
+#pragma unroll
+    for (int o = C::TPF / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_win;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = make_float2((v[n2].x - mean) * wreg[n2].x, (v[n2].y - mean) * wreg[n2].y);
+
+    ph_pass1<NFFT>(v, s_tw1, tau);
+    __syncwarp();
+    ph_x1_write<NFFT>(v, xb, tau);
+    __syncwarp();
+    ph_x1_read<NFFT>(v, xb, tau);
+    ph_pass2<NFFT>(v, s_tw2, tau);
+    if constexpr (C::R3 > 1) {
+      __syncwarp();
+      ph_x2_write<NFFT>(v, xb, tau);
+      __syncwarp();
+      ph_x2_read<NFFT>(v, xb, tau);
+      ph_pass3<NFFT>(v);
+    }
+    __syncwarp();
+    ph_z_write<NFFT>(v, xb, tau);
+    __syncwarp();
+    // power of this thread's bins -> registers, then (once every thread of the slot
+    // has read its Z pairs) into shared memory in natural order, so that the
+    // magnitude store and the band sums walk contiguous bins
+    float pk[17];
+    {
+      int q = 0;
+      ph_split_smem_cb<NFFT>(xb, tau, wtau, [&](int, float p) { pk[q++] = p; });
+    }
+    __syncwarp();
+    float* pw = reinterpret_cast<float*>(xb);  // [nb] floats, aliases the exchange buffer
+    {
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int k = tau + C::TPF * r;
+        pw[k] = pk[q++];
+        pw[C::M - k] = pk[q++];
+      }
+      if (tau == 0) pw[C::M / 2] = pk[16];
+    }
+    __syncwarp();
+    if (mag != nullptr && valid) {
+      float* mdst = mag + (((size_t)clip * n_coef + coef) * n_win + j) * nb;
+      for (int k = tau; k < nb; k += C::TPF) mdst[k] = sqrtf(pw[k]);
+    }
+    if (band != nullptr) {
+      // every slot of this warp belongs to the same (clip, window) pair (cpad is a
+      // multiple of the slots per warp); invalid slots hold zeros
+      for (int b = 0; b < n_bands; ++b) {
+        float s = 0.0f;
+        for (int k = s_blo[b] + tau; k < s_bhi[b]; k += C::TPF) s += pw[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && slot < n_slots) atomicAdd(band + pair * n_bands + b, s);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int NFFT>
+static cudaError_t launch_t(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, const float* hann,
+                            const float2* tw1, const float2* tw2, float* mag, float* band, const int* lo, const int* hi,
+                            int n_bands, int sm_count, cudaStream_t st) {
+  using C = FftCfg<NFFT>;
+  const long n_win = 1 + (T - win) / hop;
+  const long n_pairs = n_clips * n_win;
+  const int spw = 32 / C::TPF;
+  const int cpad = (n_coef + spw - 1) / spw * spw;
+  const long n_slots = n_pairs * cpad;
+  const int slots = kModThreads / C::TPF;
+  long blocks = (n_slots + slots - 1) / slots;
+  const long cap = (long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (band != nullptr) {
+    cudaError_t e = cudaMemsetAsync(band, 0, (size_t)n_pairs * n_bands * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+  }
+  const size_t smem = (size_t)(slots * C::XBUF + C::TW1 + C::TW2 + 1) * sizeof(float2);
+  cudaError_t ea = cudaFuncSetAttribute(modspec_fast_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (ea != cudaSuccess) return ea;
+  modspec_fast_kernel<NFFT><<<(unsigned)blocks, kModThreads, smem, st>>>(mfcc, n_coef, T, win, hop, n_win, n_pairs, cpad,
+                                                                     hann, tw1, tw2, mag, band, lo, hi, n_bands);
+  count_launch();
+  return cudaGetLastError();
+}
+
+bool modspec_fast_supported(int nfft) { return nfft >= 32 && nfft <= 1024; }
+
+cudaError_t modspec_fast_launch(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, int nfft,
+                                const float* hann, const float2* tw1, const float2* tw2, float* mag, float* band,
+                                const int* lo, const int* hi, int n_bands, int sm_count, cudaStream_t st) {
+  if (T < win) return cudaSuccess;
+#define MMF_MOD_CASE(N) \
+  case N: return launch_t<N>(mfcc, n_clips, n_coef, T, win, hop, hann, tw1, tw2, mag, band, lo, hi, n_bands, sm_count, st);
+  switch (nfft) {
+    MMF_MOD_CASE(32)
+    MMF_MOD_CASE(64)
+    MMF_MOD_CASE(128)
+    MMF_MOD_CASE(256)
+    MMF_MOD_CASE(512)
+    MMF_MOD_CASE(1024)
+    default: return cudaErrorInvalidValue;
+  }
+#undef MMF_MOD_CASE
+}
+
+void modspec_geometry(int nfft, StftGeometry* g) {
+  g->m = nfft / 2;
+  g->tpf = g->m / 16;
+  const int r2 = g->tpf < 16 ? g->tpf : 16;
+  g->r3 = g->tpf / r2;
+  g->tw1 = 16 * g->tpf;
+  g->tw2 = 16 * g->r3;
+  g->fpi = 0;
+}
+
+}  // namespace mmf

@@ -49,18 +49,28 @@ __global__ void __launch_bounds__(kMfccThreads)
   for (int j = 0; j < NC; ++j) acc[j] = 0.0f;
   if (valid) {
     float* col = logmel + (size_t)clip * n_mels * T + t;
-    for (int m = 0; m < n_mels; ++m) {
-      float x = col[(size_t)m * T];
-      x = fmaxf(x, thr);
-      if (clamp_in_place && own) col[(size_t)m * T] = x;
-      const float4* d4 = reinterpret_cast<const float4*>(s_dct + m * NC);
+    // 8 independent loads in flight per thread before their FMAs (the kernel is a
+    // pure stream: 4*n_mels bytes in, 8*n_mfcc bytes out per frame)
+    for (int m0 = 0; m0 < n_mels; m0 += 8) {
+      float xv[8];
 #pragma unroll
-      for (int j4 = 0; j4 < NC / 4; ++j4) {
-        const float4 d = d4[j4];
-        acc[4 * j4 + 0] = fmaf(d.x, x, acc[4 * j4 + 0]);
-        acc[4 * j4 + 1] = fmaf(d.y, x, acc[4 * j4 + 1]);
-        acc[4 * j4 + 2] = fmaf(d.z, x, acc[4 * j4 + 2]);
-        acc[4 * j4 + 3] = fmaf(d.w, x, acc[4 * j4 + 3]);
+      for (int u = 0; u < 8; ++u) xv[u] = (m0 + u < n_mels) ? __ldcs(col + (size_t)(m0 + u) * T) : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = m0 + u;
+        if (m < n_mels) {
+          const float x = fmaxf(xv[u], thr);
+          if (clamp_in_place && own) col[(size_t)m * T] = x;
+          const float4* d4 = reinterpret_cast<const float4*>(s_dct + m * NC);
+#pragma unroll
+          for (int j4 = 0; j4 < NC / 4; ++j4) {
+            const float4 d = d4[j4];
+            acc[4 * j4 + 0] = fmaf(d.x, x, acc[4 * j4 + 0]);
+            acc[4 * j4 + 1] = fmaf(d.y, x, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(d.z, x, acc[4 * j4 + 2]);
+            acc[4 * j4 + 3] = fmaf(d.w, x, acc[4 * j4 + 3]);
+          }
+        }
       }
     }
   }
@@ -125,31 +135,44 @@ cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const i
 }
 
 // ---------------------------------------------------------------------------
-// K4: scipy.signal.sosfiltfilt along time, one thread per row, float64.
+// K4: scipy.signal.sosfiltfilt along time, float64 (script/mfcc.py:402, :421).
 // Odd extension (padlen samples each side, computed in the input dtype as scipy
-// does), zi * first sample, forward cascade, same backwards, trim.  The forward
-// result of the T interior samples is parked in y and overwritten in place by
-// the backward pass; the right-hand extension lives in a per-thread tail.
+// does), zi * first sample, forward cascade, same backwards, trim.
+//
+// One warp owns 32 rows.  The recurrence is sequential in time, so each lane walks
+// its own row -- but rows are time-major in memory, so the warp stages
+// [32 rows x 32 samples] tiles through shared memory: global loads and stores are
+// coalesced 128/256-byte row segments and the per-sample loop only touches shared
+// memory.  The forward result of the T interior samples is parked in y and
+// overwritten in place by the backward pass; the forward output over the right
+// extension (needed to start the backward pass) stays in shared memory.
 // ---------------------------------------------------------------------------
-constexpr int kMaxPad = 3 * (2 * 16 + 1);
+constexpr int kSosChunk = 32;
 
 template <typename TIn, int NS>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32)
     sosfiltfilt_kernel(const TIn* __restrict__ x, long rows, long T, long x_row_stride, int group_rows,
                        long group_stride, const SosArgs a, double* __restrict__ y, long y_row_stride) {
-  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const long g = r / group_rows, gi = r - g * group_rows;
-  const TIn* xr = x + g * group_stride + gi * x_row_stride;
-  double* yr = y + r * y_row_stride;
+  extern __shared__ __align__(16) double sm_d[];
+  constexpr int CH = kSosChunk;
   const int p = a.padlen;
+  double* tile = sm_d;                    // [32][CH + 1]
+  double* tail = sm_d + 32 * (CH + 1);    // [32][p + 1]
+  long* s_off = reinterpret_cast<long*>(tail + 32 * (p + 1));  // [32] element offset of each row in x
+  const int lane = threadIdx.x;
+  const long row0 = (long)blockIdx.x * 32;
+  const int nrows = (int)min(32L, rows - row0);
   const int ns = NS > 0 ? NS : a.n_sections;
   constexpr int ZS = NS > 0 ? NS : 16;
   double z0[ZS], z1[ZS];
-  double tail[kMaxPad];
-  const TIn x0 = xr[0], xl = xr[T - 1];
-  const TIn two = (TIn)2;
 
+  {
+    const long rr = row0 + (lane < nrows ? lane : 0);
+    const long g = rr / group_rows, gi = rr - g * group_rows;
+    s_off[lane] = g * group_stride + gi * x_row_stride;
+  }
+  __syncwarp();
+  auto row_ptr = [&](int r) -> const TIn* { return x + s_off[r]; };
   auto cascade = [&](double v) -> double {
 #pragma unroll
     for (int s = 0; s < ZS; ++s) {
@@ -163,39 +186,135 @@ __global__ void __launch_bounds__(64)
     return v;
   };
 
-  // forward pass over [left ext | x | right ext]
-  const double e0 = (double)(TIn)(two * x0 - xr[p]);
-#pragma unroll
-  for (int s = 0; s < ZS; ++s)
-    if (s < ns) {
-      z0[s] = a.zi[s][0] * e0;
-      z1[s] = a.zi[s][1] * e0;
-    }
-  for (int i = 0; i < p; ++i) cascade((double)(TIn)(two * x0 - xr[p - i]));
-  for (long i = 0; i < T; ++i) yr[i] = cascade((double)xr[i]);
-  for (int j = 0; j < p; ++j) tail[j] = cascade((double)(TIn)(two * xl - xr[T - 2 - j]));
+  const bool mine = lane < nrows;
+  const TIn* xme = row_ptr(mine ? lane : 0);
+  const TIn x0 = xme[0], xl = xme[T - 1];
+  const TIn two = (TIn)2;
+  const long L = T + 2L * p;
 
-  // backward pass
-  const double f0 = tail[p - 1];
+  // Row r's sample for extended index i (odd extension computed in the input dtype).
+  // All 32 row loads of a chunk are issued back to back (32 independent requests in
+  // flight per lane) and the next chunk is fetched while the current one is filtered.
+  const TIn rx0_all = x0, rxl_all = xl;
+  auto fetch_fwd = [&](long c0, TIn (&vals)[32]) {
+    const long i = c0 + lane;
 #pragma unroll
-  for (int s = 0; s < ZS; ++s)
-    if (s < ns) {
-      z0[s] = a.zi[s][0] * f0;
-      z1[s] = a.zi[s][1] * f0;
+    for (int r = 0; r < 32; ++r) {
+      const TIn rx0 = __shfl_sync(0xffffffffu, rx0_all, r), rxl = __shfl_sync(0xffffffffu, rxl_all, r);
+      TIn v = (TIn)0;
+      if (r < nrows && i < L) {
+        const TIn* xr = x + s_off[r];
+        if (i < p) {
+          v = (TIn)(two * rx0 - xr[p - i]);
+        } else if (i < p + T) {
+          v = xr[i - p];
+        } else {
+          v = (TIn)(two * rxl - xr[T - 2 - (i - p - T)]);
+        }
+      }
+      vals[r] = v;
     }
-  for (int j = p - 1; j >= 0; --j) cascade(tail[j]);
-  for (long i = T - 1; i >= 0; --i) yr[i] = cascade(yr[i]);
+  };
+
+  // ---- forward pass over [left ext | x | right ext]
+  {
+    const double e0 = (double)(TIn)(two * x0 - xme[p]);
+#pragma unroll
+    for (int s = 0; s < ZS; ++s)
+      if (s < ns) {
+        z0[s] = a.zi[s][0] * e0;
+        z1[s] = a.zi[s][1] * e0;
+      }
+  }
+  {
+    TIn cur[32], nxt[32];
+    fetch_fwd(0, cur);
+    for (long c0 = 0; c0 < L; c0 += CH) {
+      const long i = c0 + lane;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) tile[r * (CH + 1) + lane] = (double)cur[r];
+      if (c0 + CH < L) fetch_fwd(c0 + CH, nxt);
+      __syncwarp();
+      if (mine) {
+        const int n = (int)min((long)CH, L - c0);
+        double* trow = tile + lane * (CH + 1);
+#pragma unroll 4
+        for (int k = 0; k < n; ++k) trow[k] = cascade(trow[k]);
+      }
+      __syncwarp();
+      if (i >= p && i < p + T) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r < nrows) y[(row0 + r) * y_row_stride + (i - p)] = tile[r * (CH + 1) + lane];
+      } else if (i >= p + T && i < L) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r < nrows) tail[r * (p + 1) + (int)(i - p - T)] = tile[r * (CH + 1) + lane];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) cur[r] = nxt[r];
+    }
+  }
+
+  // ---- backward pass, from the end of the right extension down to the first interior sample
+  {
+    const double f0 = tail[(mine ? lane : 0) * (p + 1) + p - 1];
+#pragma unroll
+    for (int s = 0; s < ZS; ++s)
+      if (s < ns) {
+        z0[s] = a.zi[s][0] * f0;
+        z1[s] = a.zi[s][1] * f0;
+      }
+  }
+  auto fetch_bwd = [&](long c0, double (&vals)[32]) {
+    const long i = c0 - lane;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      double v = 0.0;
+      if (r < nrows && i >= p)
+        v = i >= p + T ? tail[r * (p + 1) + (int)(i - p - T)] : y[(row0 + r) * y_row_stride + (i - p)];
+      vals[r] = v;
+    }
+  };
+  {
+    double cur[32], nxt[32];
+    fetch_bwd(L - 1, cur);
+    for (long c0 = L - 1; c0 >= p; c0 -= CH) {
+      const long i = c0 - lane;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) tile[r * (CH + 1) + lane] = cur[r];
+      if (c0 - CH >= p) fetch_bwd(c0 - CH, nxt);
+      __syncwarp();
+      if (mine) {
+        const int n = (int)min((long)CH, c0 - p + 1);
+        double* trow = tile + lane * (CH + 1);
+#pragma unroll 4
+        for (int k = 0; k < n; ++k) trow[k] = cascade(trow[k]);
+      }
+      __syncwarp();
+      if (i >= p && i < p + T) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r < nrows) y[(row0 + r) * y_row_stride + (i - p)] = tile[r * (CH + 1) + lane];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) cur[r] = nxt[r];
+    }
+  }
 }
 
 template <typename TIn>
 static cudaError_t sos_launch_t(const TIn* x, long rows, long T, long xs, int group_rows, long group_stride,
                                 const SosArgs& a, double* y, long ys, cudaStream_t st) {
-  const int threads = 64;
-  const unsigned grid = (unsigned)((rows + threads - 1) / threads);
+  const int threads = 32;
+  const unsigned grid = (unsigned)((rows + 31) / 32);
+  const size_t smem = (size_t)(32 * (kSosChunk + 1) + 32 * (a.padlen + 1) + 32) * sizeof(double);
   switch (a.n_sections) {
-#define MMF_SOS_CASE(N)                                                                                          \
-  case N:                                                                                                        \
-    sosfiltfilt_kernel<TIn, N><<<grid, threads, 0, st>>>(x, rows, T, xs, group_rows, group_stride, a, y, ys);    \
+#define MMF_SOS_CASE(N)                                                                                             \
+  case N:                                                                                                           \
+    sosfiltfilt_kernel<TIn, N><<<grid, threads, smem, st>>>(x, rows, T, xs, group_rows, group_stride, a, y, ys);    \
     break;
     MMF_SOS_CASE(1)
     MMF_SOS_CASE(2)
@@ -207,7 +326,7 @@ static cudaError_t sos_launch_t(const TIn* x, long rows, long T, long xs, int gr
     MMF_SOS_CASE(8)
 #undef MMF_SOS_CASE
     default:
-      sosfiltfilt_kernel<TIn, 0><<<grid, threads, 0, st>>>(x, rows, T, xs, group_rows, group_stride, a, y, ys);
+      sosfiltfilt_kernel<TIn, 0><<<grid, threads, smem, st>>>(x, rows, T, xs, group_rows, group_stride, a, y, ys);
   }
   count_launch();
   return cudaGetLastError();

@@ -25,7 +25,7 @@ namespace mmf {
 
 template <int NFFT>
 struct FftCfg {
-  static_assert(NFFT >= 256 && NFFT <= 4096 && (NFFT & (NFFT - 1)) == 0, "n_fft must be a power of two in [256, 4096]");
+  static_assert(NFFT >= 32 && NFFT <= 4096 && (NFFT & (NFFT - 1)) == 0, "n_fft must be a power of two in [32, 4096]");
   static constexpr int N = NFFT;
   static constexpr int M = NFFT / 2;          // complex points
   static constexpr int F = M + 1;             // real-spectrum bins
@@ -215,6 +215,27 @@ MMF_HD void ph_split_smem(const float2* xb, float* ptile, int ppitch, int t, int
     const float2 a = xb[C::M / 2];
     const float2 p = split_pair(a, a, w32(8), wtau);
     ptile[(C::M / 2) * ppitch + t] = p.x;
+  }
+}
+
+// Same, handing each (bin, power) to a callback instead of a power tile
+// (used by the trajectory-FFT kernel of the modulation spectrum).
+template <int NFFT, typename Emit>
+MMF_HD void ph_split_smem_cb(const float2* xb, int tau, float2 wtau, Emit emit) {
+  using C = FftCfg<NFFT>;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int k = tau + C::TPF * r;
+    const float2 a = xb[k];
+    const float2 b = xb[(C::M - k) & (C::M - 1)];
+    const float2 p = split_pair(a, b, w32(r), wtau);
+    emit(k, p.x);
+    emit(C::M - k, p.y);
+  }
+  if (tau == 0) {
+    const float2 a = xb[C::M / 2];
+    const float2 p = split_pair(a, a, w32(8), wtau);
+    emit(C::M / 2, p.x);
   }
 }
 

@@ -82,6 +82,9 @@ static void run(const float* y, long n, int hop, const float* window, float* pow
 extern "C" int emu_stft_power(const float* y, long n, int nfft, int hop, const float* window, float* power, long T,
                               int regs_split) {
   switch (nfft) {
+    case 32: run<32>(y, n, hop, window, power, T, regs_split); break;
+    case 64: run<64>(y, n, hop, window, power, T, regs_split); break;
+    case 128: run<128>(y, n, hop, window, power, T, regs_split); break;
     case 256: run<256>(y, n, hop, window, power, T, regs_split); break;
     case 512: run<512>(y, n, hop, window, power, T, regs_split); break;
     case 1024: run<1024>(y, n, hop, window, power, T, regs_split); break;

@@ -158,11 +158,11 @@ def test_rms_envelope_known_answer():
 def test_modulation_spectrum_known_answer():
     fr, T = 100.0, 1001
     t = np.arange(T) / fr
-    M = np.stack([3.0 + 2.0 * np.sin(2 * np.pi * 4.0 * t), np.zeros(T)])
+    M = np.stack([3.0 + 2.0 * np.sin(2 * np.pi * 5.0 * t), np.zeros(T)])
     mag, E, freqs = oracle.modulation_spectrum(M, fr)
     assert mag.shape == (2, 19, 65) and E.shape == (19, 5)
     k = np.argmax(mag[0, 3])
-    assert abs(freqs[k] - 4.0) < fr / 128
+    assert abs(freqs[k] - 5.0) < fr / 128
     assert np.all(mag[1] == 0)
     assert np.argmax(E[3]) == 2  # the [4, 8) Hz band
     # mean removal: a constant trajectory has no modulation energy
