@@ -59,6 +59,7 @@ typedef struct {
 
 #define MMF_FLAG_NO_TMA 1      /* load PCM spans with plain coalesced loads instead of TMA */
 #define MMF_FLAG_SPLIT_SMEM 2  /* n_fft = 512: pair bins through shared memory instead of shuffles */
+#define MMF_FLAG_UNFUSED_CHANGE 4 /* composite calls: separate filter / derivative kernels instead of the fused one */
 
 typedef struct mmf_plan mmf_plan;
 

@@ -17,8 +17,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmmf_b200.so"
-SOURCES = ["stft_mel.cu", "post_kernels.cu", "modspec_fast.cu", "c_api.cu", "host_tables.cpp"]
-HEADERS = ["fft_regs.cuh", "stft_core.cuh", "mmf_internal.h", "../../include/mmf.h"]
+SOURCES = ["stft_mel.cu", "post_kernels.cu", "change_fused.cu", "modspec_fast.cu", "c_api.cu", "host_tables.cpp"]
+HEADERS = ["fft_regs.cuh", "stft_core.cuh", "sos_par.cuh", "mmf_internal.h", "../../include/mmf.h"]
 
 NVCC_FLAGS = [
     "-gencode",
@@ -48,6 +48,7 @@ MMF_ERR_NOMEM = -5
 
 MMF_FLAG_NO_TMA = 1
 MMF_FLAG_SPLIT_SMEM = 2
+MMF_FLAG_UNFUSED_CHANGE = 4
 
 
 class mmf_config(C.Structure):
@@ -91,19 +92,25 @@ class mmf_modspec_params(C.Structure):
     ]
 
 
-def needs_build() -> bool:
-    if not LIB_PATH.exists():
+OBJ_DIR = PKG_DIR / "build"
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
-    for f in SOURCES + HEADERS:
-        p = (CSRC / f).resolve()
-        if p.exists() and p.stat().st_mtime > t:
-            return True
-    return False
+    t = target.stat().st_mtime
+    return any(p.exists() and p.stat().st_mtime > t for p in deps)
+
+
+def needs_build() -> bool:
+    return _stale(LIB_PATH, [(CSRC / f).resolve() for f in SOURCES + HEADERS])
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source of the package for sm_100a into ``libmmf_b200.so``."""
+    """Compile every CUDA source of the package for sm_100a into ``libmmf_b200.so``.
+
+    One object per source (compiled in parallel, rebuilt only when the source or a
+    header is newer), then one link step."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -111,15 +118,30 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if LIB_PATH.exists():  # GPU box without a toolkit: use the prebuilt file that travelled with the repo
             return LIB_PATH
         raise RuntimeError("nvcc not found and libmmf_b200.so is missing")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
+    from concurrent.futures import ThreadPoolExecutor
+
+    OBJ_DIR.mkdir(exist_ok=True)
+    headers = [(CSRC / h).resolve() for h in HEADERS]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src: str):
+        obj = OBJ_DIR / (Path(src).stem + ".o")
+        if not force and not _stale(obj, [CSRC / src, *headers]):
+            return obj, ""
+        cmd = [nvcc, *compile_flags, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(obj), str(CSRC / src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        print("".join(log for _, log in results))
+    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *[str(o) for o, _ in results]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

@@ -336,6 +336,7 @@ def get_MFCCS_change_batch(
     preemph=0.0,
     return_features=False,
     device=None,
+    flags=0,
 ):
     """``get_MFCCS_change`` for a batch ``[B, N]`` of equal-length clips.
 
@@ -343,7 +344,7 @@ def get_MFCCS_change_batch(
     the result is returned as CUDA tensors).  Returns ``(totChange [B, T], T [T])``
     and, with ``return_features``, a dict with ``logmel``, ``mfcc``, ``delta``."""
     torch = _torch()
-    plan = _change_setup(sigSr, tStep, winLen, n_mfcc, n_fft, minFreq, maxFreq, n_mels, preemph, device)
+    plan = _change_setup(sigSr, tStep, winLen, n_mfcc, n_fft, minFreq, maxFreq, n_mels, preemph, device, flags)
     cutOffNorm = filtCutoff / ((1 / tStep) / 2)  # script/mfcc.py:398
     sos = scipy.signal.butter(filtOrd, cutOffNorm, btype="low", output="sos")  # script/mfcc.py:400
     method = 0 if diffMethod == "grad" else 1

@@ -6,6 +6,7 @@
 #include <cudaTypedefs.h>
 
 #include "mmf_internal.h"
+#include "sos_par.cuh"
 
 namespace mmf {
 
@@ -430,6 +431,16 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   return MMF_OK;
 }
 
+// zero-phase IIR over independent rows: chunk-parallel kernel when the extended row
+// fits in shared memory (<= 2080 samples, <= 4 sections), else the sequential one
+static cudaError_t sosfiltfilt_any(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
+                                   long group_stride, const SosArgs& a, double* y, long ys, cudaStream_t st) {
+  SosPar par;
+  if (sos_par_fill(a, T, &par))
+    return sosfiltfilt_par_launch(x, x_is_f32, rows, T, xs, group_rows, group_stride, par, y, ys, st);
+  return sosfiltfilt_launch_grouped(x, x_is_f32, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+}
+
 }  // namespace mmf
 
 extern "C" {
@@ -479,8 +490,9 @@ int mmf_sosfiltfilt(mmf_plan* plan, const void* x_dev, int32_t x_is_f32, int64_t
     return fail(MMF_ERR_TOO_SHORT, buf);
   }
   MMF_CUDA(cudaSetDevice(plan->cfg.device));
-  cudaError_t e = sosfiltfilt_launch(x_dev, x_is_f32, rows, T, x_row_stride, a, y_dev, y_row_stride,
-                                     (cudaStream_t)stream);
+  cudaError_t e = sosfiltfilt_any(x_dev, x_is_f32, rows, T, x_row_stride,
+                                  (int)(rows > 0x7fffffffL ? 0x7fffffff : rows), 0, a, y_dev, y_row_stride,
+                                  (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "sosfiltfilt_kernel launch");
   return MMF_OK;
 }
@@ -627,17 +639,29 @@ static int run_post(mmf_plan* p, unsigned char*& cur, float* logmel, const int* 
   if (T <= sa.padlen) return too_short(sa.padlen);
   if (prm->out_kind == 0 && T <= so.padlen) return too_short(so.padlen);
   float* mfcc = mfcc_out ? mfcc_out : (float*)carve(cur, (size_t)n_clips * c.n_mfcc * T * 4);
+  if ((rc = mmf_mfcc(p, logmel, clipmax, n_clips, T, mfcc, delta_out, clamp_in_place, st))) return rc;
+  // fused per-clip kernel: row filters, derivative + norm and the output filter with the
+  // float64 rows resident in shared memory (script/mfcc.py:393-425)
+  SosPar pa, po;
+  size_t fsmem = 0;
+  const bool out_iir = prm->out_kind == 0;
+  if (!(c.flags & MMF_FLAG_UNFUSED_CHANGE) && sos_par_fill(sa, T, &pa) && (!out_iir || sos_par_fill(so, T, &po)) &&
+      change_fused_supported(pa, out_iir ? &po : nullptr, rows, T, &fsmem)) {
+    cudaError_t e = change_fused_launch(mfcc, n_clips, c.n_mfcc, first, rows, T, prm->diff_method, pa,
+                                        out_iir ? po : pa, prm->out_kind, tot, fsmem, st);
+    if (e == cudaSuccess) return MMF_OK;
+    if (e != cudaErrorNotSupported) return cuda_fail(e, "change_fused_kernel launch");
+  }
   double* filt = (double*)carve(cur, (size_t)n_clips * rows * T * 8);
   double* raw = (double*)carve(cur, (size_t)n_clips * T * 8);
-  if ((rc = mmf_mfcc(p, logmel, clipmax, n_clips, T, mfcc, delta_out, clamp_in_place, st))) return rc;
   // Butterworth zero-phase low-pass of rows first..n_mfcc-1 of every clip (script/mfcc.py:398-402)
-  cudaError_t e = sosfiltfilt_launch_grouped(mfcc + (size_t)first * T, 1, n_clips * rows, T, T, rows,
-                                             (long)c.n_mfcc * T, sa, filt, T, st);
+  cudaError_t e = sosfiltfilt_any(mfcc + (size_t)first * T, 1, n_clips * rows, T, T, rows, (long)c.n_mfcc * T, sa,
+                                  filt, T, st);
   if (e != cudaSuccess) return cuda_fail(e, "sosfiltfilt (mfcc rows)");
-  double* change = prm->out_kind == 0 ? raw : tot;
+  double* change = out_iir ? raw : tot;
   if ((rc = mmf_delta_norm(p, filt, n_clips, rows, T, prm->diff_method, change, st))) return rc;
-  if (prm->out_kind == 0) {
-    e = sosfiltfilt_launch(raw, 0, n_clips, T, T, so, tot, T, st);
+  if (out_iir) {
+    e = sosfiltfilt_any(raw, 0, n_clips, T, T, (int)std::min<int64_t>(n_clips, 0x7fffffff), 0, so, tot, T, st);
     if (e != cudaSuccess) return cuda_fail(e, "sosfiltfilt (total change)");
   }
   return MMF_OK;

@@ -1,0 +1,240 @@
+// K4 (chunk-parallel) and the fused K4+K5+K4 "change" kernel.
+//
+//  * sosfiltfilt_par_kernel: scipy.signal.sosfiltfilt for independent rows whose
+//    odd-extended length fits in shared memory; one warp per row (sos_par.cuh).
+//  * change_fused_kernel: everything after the MFCC in get_MFCCS_change
+//    (script/mfcc.py:393-425) for one clip per CTA: zero-phase Butterworth of every
+//    kept coefficient row (one warp per row, rows stay in shared memory),
+//    derivative + norm over rows (script/mfcc.py:405-415), and the zero-phase
+//    output filter of the resulting curve (script/mfcc.py:417-425) -- the
+//    float64 intermediates (96 KB per 10 s clip) never touch HBM.
+#include <algorithm>
+#include <cstring>
+
+#include "mmf_internal.h"
+#include "sos_par.cuh"
+
+namespace mmf {
+
+// ---------------------------------------------------------------------------
+// host: chunk geometry and the zero-input transition matrices
+// ---------------------------------------------------------------------------
+static void host_sos_step(const SosPar& a, double v, double* z) {
+  for (int s = 0; s < a.ns; ++s) {
+    const double out = std::fma(a.sos[s][0], v, z[2 * s]);
+    z[2 * s] = std::fma(a.sos[s][1], v, std::fma(-a.sos[s][4], out, z[2 * s + 1]));
+    z[2 * s + 1] = std::fma(a.sos[s][2], v, -a.sos[s][5] * out);
+    v = out;
+  }
+}
+
+bool sos_par_fill(const SosArgs& src, long T, SosPar* out) {
+  if (src.n_sections < 1 || src.n_sections > kParMaxSections) return false;
+  const long L = T + 2L * src.padlen;
+  if (L > 32L * kSosParMaxChunk) return false;
+  std::memset(out, 0, sizeof(*out));
+  out->ns = src.n_sections;
+  out->padlen = src.padlen;
+  int cl = (int)((L + 31) / 32);
+  if ((cl & 1) == 0) ++cl;
+  out->CL = cl;
+  for (int s = 0; s < src.n_sections; ++s) {
+    for (int k = 0; k < 6; ++k) out->sos[s][k] = src.sos[s][k];
+    out->zi[s][0] = src.zi[s][0];
+    out->zi[s][1] = src.zi[s][1];
+  }
+  const int D = 2 * src.n_sections;
+  for (int jj = 0; jj < 5; ++jj) {
+    const long steps = (long)cl << jj;
+    for (int c = 0; c < D; ++c) {
+      double z[2 * kParMaxSections] = {0};
+      z[c] = 1.0;
+      for (long i = 0; i < steps; ++i) host_sos_step(*out, 0.0, z);
+      for (int r = 0; r < D; ++r) out->mpow[jj][r][c] = z[r];
+    }
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// generic rows
+// ---------------------------------------------------------------------------
+constexpr int kParWarps = 4;
+constexpr int kFusedPerThread = 9;
+constexpr int kFusedMaxWarps = 12;  // 384 threads, <= 85 registers: two CTAs per SM
+
+template <typename TIn, int NS>
+__global__ void __launch_bounds__(kParWarps * 32)
+    sosfiltfilt_par_kernel(const TIn* __restrict__ x, long rows, int T, long x_row_stride, int group_rows,
+                           long group_stride, const __grid_constant__ SosPar a, double* __restrict__ y,
+                           long y_row_stride) {
+  extern __shared__ __align__(16) double sm_par[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long row = (long)blockIdx.x * kParWarps + warp;
+  if (row >= rows) return;
+  const int S = 32 * a.CL, p = a.padlen, L = T + 2 * p;
+  double* buf = sm_par + (size_t)warp * S;
+  const long g = row / group_rows, gi = row - g * group_rows;
+  warp_load_odd_ext<TIn>(x + g * group_stride + gi * x_row_stride, T, p, buf, S, lane);
+  const SosRegs<NS> c(a);
+  warp_sosfiltfilt<NS>(buf, L, a, c, lane);
+  double* dst = y + row * y_row_stride;
+  for (int t = lane; t < T; t += 32) dst[t] = buf[p + t];
+}
+
+template <typename TIn, int NS>
+static cudaError_t par_launch_ns(const TIn* x, long rows, long T, long xs, int group_rows, long group_stride,
+                                 const SosPar& a, double* y, long ys, cudaStream_t st) {
+  const unsigned grid = (unsigned)((rows + kParWarps - 1) / kParWarps);
+  const size_t smem = (size_t)kParWarps * 32 * a.CL * sizeof(double);
+  auto kfn = sosfiltfilt_par_kernel<TIn, NS>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  kfn<<<grid, kParWarps * 32, smem, st>>>(x, rows, (int)T, xs, group_rows, group_stride, a, y, ys);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <typename TIn>
+static cudaError_t par_launch_t(const TIn* x, long rows, long T, long xs, int group_rows, long group_stride,
+                                const SosPar& a, double* y, long ys, cudaStream_t st) {
+  switch (a.ns) {
+    case 1: return par_launch_ns<TIn, 1>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    case 2: return par_launch_ns<TIn, 2>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    case 3: return par_launch_ns<TIn, 3>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    case 4: return par_launch_ns<TIn, 4>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t sosfiltfilt_par_launch(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
+                                   long group_stride, const SosPar& a, double* y, long ys, cudaStream_t st) {
+  if (x_is_f32) return par_launch_t<float>((const float*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+  return par_launch_t<double>((const double*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+}
+
+// ---------------------------------------------------------------------------
+// fused per-clip kernel
+// ---------------------------------------------------------------------------
+template <int NS1, int NS2>
+__global__ void __launch_bounds__(kFusedMaxWarps * 32, 2)
+    change_fused_kernel(const float* __restrict__ mfcc, int n_mfcc, int first, int rows, int T, int method,
+                        const __grid_constant__ SosPar a1, const __grid_constant__ SosPar a2, int out_kind,
+                        double* __restrict__ tot) {
+  extern __shared__ __align__(16) double sm_fused[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const long clip = blockIdx.x;
+  const int S = 32 * a1.CL, p = a1.padlen, L = T + 2 * p;
+  // 1. zero-phase Butterworth of every kept coefficient row, in place in shared memory
+  {
+    const SosRegs<NS1> c1(a1);
+    for (int r = warp; r < rows; r += nwarps) {
+      double* buf = sm_fused + (size_t)r * S;
+      warp_load_odd_ext<float>(mfcc + ((size_t)clip * n_mfcc + first + r) * T, T, p, buf, S, lane);
+      warp_sosfiltfilt<NS1>(buf, L, a1, c1, lane);
+    }
+  }
+  __syncthreads();
+  // 2. derivative along time and norm over rows (script/mfcc.py:405-415)
+  constexpr int kPerThread = kFusedPerThread;  // the launcher guarantees T <= blockDim * kPerThread
+  double raw[kPerThread];
+#pragma unroll
+  for (int q = 0; q < kPerThread; ++q) {
+    const int t = tid + q * blockDim.x;
+    double s = 0.0;
+    if (t < T) {
+      for (int r = 0; r < rows; ++r) {
+        const double* f = sm_fused + (size_t)r * S + p;
+        double d;
+        if (T == 1) {
+          d = 0.0;
+        } else if (t == 0) {
+          d = (method == 0 || T < 3) ? f[1] - f[0] : (-3.0 * f[0] + 4.0 * f[1] - f[2]) / 2.0;
+        } else if (t == T - 1) {
+          d = (method == 0 || T < 3) ? f[T - 1] - f[T - 2] : (3.0 * f[T - 1] - 4.0 * f[T - 2] + f[T - 3]) / 2.0;
+        } else {
+          d = (f[t + 1] - f[t - 1]) / 2.0;
+        }
+        s += d * d;
+      }
+    }
+    raw[q] = sqrt(s) / (double)rows;
+  }
+  double* dst = tot + (size_t)clip * T;
+  if (out_kind != 0) {
+#pragma unroll
+    for (int q = 0; q < kPerThread; ++q) {
+      const int t = tid + q * blockDim.x;
+      if (t < T) dst[t] = raw[q];
+    }
+    return;
+  }
+  __syncthreads();  // every row has been read: row 0's buffer becomes the curve's buffer
+  // 3. output filter of the curve (script/mfcc.py:417-425); the two cascades may differ in padlen
+  const int p2 = a2.padlen, L2 = T + 2 * p2, S2 = 32 * a2.CL;
+  double* cbuf = sm_fused;
+#pragma unroll
+  for (int q = 0; q < kPerThread; ++q) {
+    const int t = tid + q * blockDim.x;
+    if (t < T) cbuf[p2 + t] = raw[q];
+  }
+  __syncthreads();
+  for (int i = tid; i < S2; i += blockDim.x) {
+    if (i < p2) {
+      cbuf[i] = 2.0 * cbuf[p2] - cbuf[p2 + (p2 - i)];
+    } else if (i >= p2 + T) {
+      cbuf[i] = i < L2 ? 2.0 * cbuf[p2 + T - 1] - cbuf[p2 + T - 2 - (i - p2 - T)] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const SosRegs<NS2> c2(a2);
+    warp_sosfiltfilt<NS2>(cbuf, L2, a2, c2, lane);
+  }
+  __syncthreads();
+  for (int t = tid; t < T; t += blockDim.x) dst[t] = cbuf[p2 + t];
+}
+
+bool change_fused_supported(const SosPar& a1, const SosPar* a2, int rows, long T, size_t* smem_out) {
+  if (rows < 1 || T < 1 || T > (long)kFusedMaxWarps * 32 * kFusedPerThread) return false;
+  size_t doubles = (size_t)rows * 32 * a1.CL;
+  if (a2) doubles = std::max(doubles, (size_t)32 * a2->CL);
+  const size_t smem = doubles * sizeof(double);
+  if (smem > 220 * 1024) return false;
+  if (smem_out) *smem_out = smem;
+  return true;
+}
+
+template <int NS1, int NS2>
+static cudaError_t fused_launch_cl(const float* mfcc, long n_clips, int n_mfcc, int first, int rows, long T,
+                                   int method, const SosPar& a1, const SosPar& a2, int out_kind, double* tot,
+                                   size_t smem, cudaStream_t st) {
+  // >= ceil(T / (32*kFusedPerThread)) warps for the derivative phase, one per row if possible
+  const int warps = std::min(kFusedMaxWarps, std::max(rows, (int)((T + 32 * kFusedPerThread - 1) / (32 * kFusedPerThread))));
+  auto kfn = change_fused_kernel<NS1, NS2>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) return e;
+  kfn<<<(unsigned)n_clips, warps * 32, smem, st>>>(mfcc, n_mfcc, first, rows, (int)T, method, a1, a2, out_kind, tot);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t change_fused_launch(const float* mfcc, long n_clips, int n_mfcc, int first, int rows, long T, int method,
+                                const SosPar& a1, const SosPar& a2, int out_kind, double* tot, size_t smem,
+                                cudaStream_t st) {
+  // equal section counts (the reference's default: outFilter None reuses the row filter, 'iir' uses
+  // the same order) get an instantiation; anything else goes through the unfused kernels
+  const int k = a1.ns * 10 + (out_kind == 0 ? a2.ns : a1.ns);
+  switch (k) {
+#define MMF_FUSED_CASE(A, B) \
+  case A * 10 + B: return fused_launch_cl<A, B>(mfcc, n_clips, n_mfcc, first, rows, T, method, a1, a2, out_kind, tot, smem, st);
+    MMF_FUSED_CASE(1, 1)
+    MMF_FUSED_CASE(2, 2)
+    MMF_FUSED_CASE(3, 3)
+    MMF_FUSED_CASE(4, 4)
+#undef MMF_FUSED_CASE
+    default: return cudaErrorNotSupported;
+  }
+}
+
+}  // namespace mmf

@@ -69,6 +69,16 @@ cudaError_t sosfiltfilt_launch(const void* x, int x_is_f32, long rows, long T, l
                                long ys, cudaStream_t st);
 cudaError_t sosfiltfilt_launch_grouped(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
                                        long group_stride, const SosArgs& a, double* y, long ys, cudaStream_t st);
+// chunk-parallel zero-phase IIR and the fused per-clip change kernel (change_fused.cu)
+constexpr int kSosParMaxChunk = 191;  // rows up to 32*191 = 6112 extended samples stay in shared memory
+struct SosPar;
+bool sos_par_fill(const SosArgs& src, long T, SosPar* out);
+cudaError_t sosfiltfilt_par_launch(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
+                                   long group_stride, const SosPar& a, double* y, long ys, cudaStream_t st);
+bool change_fused_supported(const SosPar& a1, const SosPar* a2, int rows, long T, size_t* smem_out);
+cudaError_t change_fused_launch(const float* mfcc, long n_clips, int n_mfcc, int first, int rows, long T, int method,
+                                const SosPar& a1, const SosPar& a2, int out_kind, double* tot, size_t smem,
+                                cudaStream_t st);
 cudaError_t delta_norm_launch(const double* x, long n_clips, int rows, long T, int method, double* tot,
                               cudaStream_t st);
 cudaError_t fir_filtfilt_launch(const double* x, long rows, long T, const double* b_dev, int n_taps, double* y,

@@ -173,6 +173,45 @@ def test_sosfiltfilt_bandpass_and_too_short(cuda_device):
     assert "greater than padlen, which is 21" in ei.value.msg
 
 
+@pytest.mark.parametrize("T", [22, 45, 333, 1001, 2001, 2038, 2039, 5000])
+@pytest.mark.parametrize("order", [2, 6, 8, 10])
+def test_sosfiltfilt_chunk_parallel_and_sequential_paths(T, order, cuda_device):
+    """Rows with T + 2*padlen <= 2080 and <= 4 sections take the chunk-parallel
+    kernel (one warp per row, exact state carry across 32 chunks); longer rows or
+    higher orders take the sequential kernel.  Both must equal scipy."""
+    torch = _torch()
+    rng = np.random.default_rng(100 + T + order)
+    x = (rng.standard_normal((7, T)).cumsum(axis=-1) + 3.0).astype(np.float32)
+    sos = scipy.signal.butter(order, 0.24, output="sos")
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    padlen = 3 * (2 * len(sos) + 1 - min((sos[:, 2] == 0).sum(), (sos[:, 5] == 0).sum()))
+    if T <= padlen:
+        with pytest.raises(mm.MmfError):
+            plan.sosfiltfilt(torch.as_tensor(x).cuda(), sos)
+        return
+    y = plan.sosfiltfilt(torch.as_tensor(x).cuda(), sos).cpu().numpy()
+    ref = scipy.signal.sosfiltfilt(sos, x)
+    assert np.max(np.abs(y - ref)) < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_fused_change_kernel_equals_unfused(cuda_device):
+    """change_fused_kernel (rows resident in shared memory) against the separate
+    filter / derivative / filter kernels (MMF_FLAG_UNFUSED_CHANGE) and the oracle."""
+    sr = 16000
+    y = synth_batch(40, 5, sr * 10, sr)
+    kw = dict(tStep=0.01, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=0, maxFreq=8000, outFiltCutOff=[12], n_mels=40)
+    for over in (dict(), dict(outFilter=None), dict(diffMethod="sg"), dict(removeFirst=0), dict(filtOrd=4, outFiltLen=4),
+                 dict(filtOrd=8, outFiltLen=8), dict(outFiltLen=2)):
+        k = {**kw, **over}
+        fused, T = mm.get_MFCCS_change_batch(y, sr, **k)
+        unfused, _ = mm.get_MFCCS_change_batch(y, sr, flags=_lib.MMF_FLAG_UNFUSED_CHANGE, **k)
+        assert np.max(np.abs(fused - unfused)) < 1e-11, over
+        for i in (0, 4):
+            ref, Tref = oracle.get_MFCCS_change(y[i], sr, **k)
+            assert np.array_equal(T, Tref)
+            assert np.max(np.abs(fused[i] - ref)) < ABS_TOL, over
+
+
 KW_GUI = dict(channelN=0, tStep=0.005, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=100, maxFreq=10000, removeFirst=1,
               filtCutoff=12, filtOrd=6, diffMethod="grad", outFilter="iir", outFiltType="low", outFiltCutOff=[12],
               outFiltLen=6, outFiltPolyOrd=3)

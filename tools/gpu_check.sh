@@ -1,5 +1,13 @@
+#!/bin/bash
+# Usage (on the GPU box, via gpurun): bash tools/gpu_check.sh [tag]
+# GPU parity tests, then a bench line, written under gpurun_out/.
+tag=${1:-run}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 2>&1 | tail -12 > gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/bench2.json 2> gpurun_out/bench2.err; echo "bench rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench2.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['kernel_ms'], d['roofline']['frac'])"; tail -3 gpurun_out/bench2.err
-python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"mfcc_kernel|sosfilt|delta_norm|modspec|stft_mel|fill_i32" -s 21 -c 7 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu1.log 2>&1; echo rc=$?
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -15 > gpurun_out/pytest_gpu_$tag.log; tail -4 gpurun_out/pytest_gpu_$tag.log
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench_$tag.json'))
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'], 'k1_ms', d['roofline']['kernel_ms'], 'frac', d['roofline']['frac'])
+PY
+tail -3 gpurun_out/bench_$tag.err
