@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cudaTypedefs.h>
 
@@ -255,40 +256,53 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     }
     return pp;
   };
-  auto smem_for = [&](int tf, int pt_bufs) {
+  auto smem_for = [&](int tf, int span_bufs, int pt_bufs) {
     const int span = (tf - 1) * cfg->hop_length + cfg->n_fft + p->lead + 3;
     const int alloc = (span + 255) / 256 * 256;
-    return stft_smem_bytes(cfg->n_fft, alloc, pitch_for(tf), pt_bufs, cfg->n_mels);
+    return stft_smem_bytes(cfg->n_fft, alloc, span_bufs, pitch_for(tf), pt_bufs, cfg->n_mels);
   };
-  // two CTAs per SM need <= 113 KB each (227 KB per SM, 1 KB reserved per CTA)
+  // Preference: the widest tile first (32 frames = one frame per lane in the mel phase, no
+  // divergence between band groups), then as much double buffering as two CTAs per SM allow
+  // (<= 113 KB each: 227 KB per SM, 1 KB reserved per CTA); one CTA per SM as the last resort.
   const size_t budget2 = 113 * 1024, budget1 = 226 * 1024;
-  int tf = 0, pt_bufs = 2, ctas = 2;
-  for (int cand = 32; cand >= fpi && tf == 0; cand >>= 1) {
-    if (cand % fpi) continue;
-    if (smem_for(cand, 2) <= budget2) {
-      tf = cand;
-      pt_bufs = 2;
-    } else if (smem_for(cand, 1) <= budget2) {
-      tf = cand;
-      pt_bufs = 1;
+  static const int kBufChoices[4][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}};  // {span_bufs, pt_bufs}
+  int tf = 0, pt_bufs = 2, span_bufs = 2, ctas = 2;
+  auto pick = [&](size_t budget) {
+    for (int cand = 32; cand >= 1 && tf == 0; cand >>= 1) {
+      if (cand < fpi || cand % fpi) continue;
+      for (const auto& ch : kBufChoices)
+        if (smem_for(cand, ch[0], ch[1]) <= budget) {
+          tf = cand;
+          span_bufs = ch[0];
+          pt_bufs = ch[1];
+          break;
+        }
     }
-  }
+  };
+  pick(budget2);
   if (tf == 0) {
     ctas = 1;
-    tf = std::min(32, fpi);
-    pt_bufs = smem_for(tf, 2) <= budget1 ? 2 : 1;
-    if (fpi > 32 || smem_for(tf, pt_bufs) > budget1) {
-      delete p;
-      return fail(MMF_ERR_UNSUPPORTED, "hop_length/n_fft combination needs more shared memory than one SM has");
-    }
+    pick(budget1);
+  }
+  // debugging / tuning overrides
+  if (const char* e = std::getenv("MMF_TF")) {
+    const int v = std::atoi(e);
+    if (v >= fpi && v <= 32 && (v & (v - 1)) == 0 && v % fpi == 0) tf = v;
+    if (const char* e2 = std::getenv("MMF_SPAN_BUFS")) span_bufs = std::atoi(e2) == 1 ? 1 : 2;
+    if (const char* e3 = std::getenv("MMF_PT_BUFS")) pt_bufs = std::atoi(e3) == 1 ? 1 : 2;
+    ctas = smem_for(tf, span_bufs, pt_bufs) <= budget2 ? 2 : 1;
+    if (smem_for(tf, span_bufs, pt_bufs) > budget1) tf = 0;
+  }
+  if (tf == 0 || fpi > 32) {
+    delete p;
+    return fail(MMF_ERR_UNSUPPORTED, "hop_length/n_fft combination needs more shared memory than one SM has");
   }
   p->TF = tf;
   p->pt_bufs = pt_bufs;
+  p->span_bufs = span_bufs;
   p->ctas_per_sm = ctas;
   p->ppitch = pitch_for(tf);
-  p->smem = smem_for(tf, pt_bufs);
-  const int workers = 8 * (32 / tf);
-  p->bands_per_worker = (cfg->n_mels + workers - 1) / workers;
+  p->smem = smem_for(tf, span_bufs, pt_bufs);
 
   // ---- constant tables
   std::vector<float> window, mel, dct;
@@ -301,6 +315,38 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     return fail(MMF_ERR_UNSUPPORTED, "mel filterbank is not a two-slope (triangular) bank");
   }
   host_dct(cfg->n_mfcc, cfg->n_mels, dct);
+  // ---- mel band groups: 8 warps * (32 / TF) workers, contiguous bands each, balanced on
+  // cost = bins walked + bands emitted (smallest achievable maximum, greedy fill under a
+  // binary-searched bound)
+  std::vector<int> band_split(257, cfg->n_mels);
+  {
+    const int workers = std::min(256, 8 * (32 / tf));
+    const int cbin = 7, cband = 48;  // measured: 7 instructions per bin, 29 per segment + 19 per band
+    auto group_cost = [&](int a, int b) {  // bands [a, b): segments a..b
+      return cbin * (sp.seg_start[b + 1] - sp.seg_start[a]) + cband * (b - a);
+    };
+    auto fill = [&](long bound, std::vector<int>* out) {
+      int a = 0, used = 0;
+      while (a < cfg->n_mels) {
+        if (used == workers) return false;
+        int b = a + 1;
+        if (group_cost(a, b) > bound) return false;
+        while (b < cfg->n_mels && group_cost(a, b + 1) <= bound) ++b;
+        if (out) (*out)[used] = a;
+        a = b;
+        ++used;
+      }
+      if (out)
+        for (int w = used; w < 257; ++w) (*out)[w] = cfg->n_mels;
+      return true;
+    };
+    long lo = 0, hi = group_cost(0, cfg->n_mels);
+    while (lo < hi) {
+      const long mid = (lo + hi) / 2;
+      if (fill(mid, nullptr)) hi = mid; else lo = mid + 1;
+    }
+    fill(lo, &band_split);
+  }
   std::vector<float2> tw1, tw2;
   host_twiddles(cfg->n_fft, p->geo, tw1, tw2);
   p->nc_pad = cfg->n_mfcc <= 16 ? 16 : (cfg->n_mfcc <= 32 ? 32 : (cfg->n_mfcc <= 64 ? 64 : 128));
@@ -313,6 +359,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   cudaError_t e;
   if ((e = upload(&p->d_window, window)) != cudaSuccess || (e = upload(&p->d_tw1, tw1)) != cudaSuccess ||
       (e = upload(&p->d_tw2, tw2)) != cudaSuccess || (e = upload(&p->d_seg, sp.seg_start)) != cudaSuccess ||
+      (e = upload(&p->d_band_split, band_split)) != cudaSuccess ||
       (e = upload(&p->d_w2, w2)) != cudaSuccess || (e = upload(&p->d_dct, dct_pad)) != cudaSuccess) {
     mmf_plan_destroy(p);
     return cuda_fail(e, "uploading plan constants");
@@ -337,6 +384,7 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_tw1);
   cudaFree(p->d_tw2);
   cudaFree(p->d_seg);
+  cudaFree(p->d_band_split);
   cudaFree(p->d_w2);
   cudaFree(p->d_dct);
   cudaFree(p->ws);
@@ -387,16 +435,17 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   a.span_alloc = (a.span_floats + 255) / 256 * 256;
   a.ppitch = p->ppitch;
   a.pt_bufs = p->pt_bufs;
+  a.span_bufs = p->span_bufs;
   a.vec_ok = (c.hop_length % 2 == 0) ? 1 : 0;
   a.split_regs = (c.n_fft == 512 && !(c.flags & MMF_FLAG_SPLIT_SMEM)) ? 1 : 0;
   a.n_mels = c.n_mels;
-  a.bands_per_worker = p->bands_per_worker;
   a.amin = c.amin;
   a.preemph = c.preemph;
   a.window = p->d_window;
   a.tw1 = p->d_tw1;
   a.tw2 = p->d_tw2;
   a.seg_start = p->d_seg;
+  a.band_split = p->d_band_split;
   a.w2 = p->d_w2;
   a.logmel = logmel;
   a.clipmax = clipmax;

@@ -27,18 +27,19 @@ struct StftArgs {
   int span_alloc;        // span_floats rounded up to 256-float TMA boxes
   int ppitch;            // power-tile row pitch (floats)
   int pt_bufs;           // power-tile buffers (2 = double buffered, 1 = extra barrier per tile)
+  int span_bufs;         // PCM span buffers (2 = prefetch at tile start, 1 = prefetch after the FFT phase)
   int lead;              // samples loaded ahead of the first frame (2 when pre-emphasis is on)
   int use_tma;
   int vec_ok;            // 64-bit shared loads allowed (hop even)
   int split_regs;        // n_fft = 512: shuffle-based split step
   int n_mels;
-  int bands_per_worker;
   float amin;
   float preemph;
   const float* window;   // [n_fft]
   const float2* tw1;     // [16*TPF]
   const float2* tw2;     // [16*R3]
   const int* seg_start;  // [n_mels + 2]
+  const int* band_split; // [257] first band of each mel worker (balanced band groups), padded with n_mels
   const float2* w2;      // [F] (falling, rising) mel weights per bin
   float* logmel;         // [n_clips, n_mels, T] or null
   int* clipmax;          // [n_clips] float keys or null
@@ -50,7 +51,7 @@ struct StftGeometry {
 };
 
 int stft_geometry(int n_fft, StftGeometry* g);
-size_t stft_smem_bytes(int n_fft, int span_alloc, int ppitch, int pt_bufs, int n_mels);
+size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int n_mels);
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
                             cudaStream_t st);
 
@@ -121,13 +122,14 @@ struct mmf_plan {
   int sm_count;
   mmf::StftGeometry geo;
   // tile geometry
-  int TF, ppitch, pt_bufs, ctas_per_sm, lead, bands_per_worker;
+  int TF, ppitch, pt_bufs, span_bufs, ctas_per_sm, lead;
   size_t smem;
   // device constants
   float* d_window = nullptr;
   float2* d_tw1 = nullptr;
   float2* d_tw2 = nullptr;
   int* d_seg = nullptr;
+  int* d_band_split = nullptr;
   float2* d_w2 = nullptr;
   float* d_dct = nullptr;  // [n_mels][nc_pad]
   int nc_pad = 0;

@@ -264,19 +264,40 @@ MMF_HD void ph_split_regs512(const float2 (&v)[16], const float2 (&bpart)[8], fl
 // is stored sparsely: bin k lies in segment seg(k) (between two filter centres)
 // and feeds at most filter seg-1 (falling slope, w2[k].x) and filter seg
 // (rising slope, w2[k].y).  seg_start[j] = first bin of segment j.
-// Calls emit(m, value) for every band.
-template <typename Emit>
-MMF_HD void mel_column(const float* ptile, int ppitch, int t, const int* seg_start, const float2* w2, int m0, int m1,
+// pcol points at the column's bin 0 (bins are PITCH floats apart; PITCH = 0 takes
+// the run-time ppitch).  Calls emit(m, value) for every band, in ascending order.
+template <int PITCH, typename Emit>
+MMF_HD void mel_column(const float* pcol, int ppitch, const int* seg_start, const float2* w2, int m0, int m1,
                        Emit emit) {
+  const int pitch = PITCH > 0 ? PITCH : ppitch;
   float up_prev = 0.0f;
+  int k = seg_start[m0];
+  const float* pp = pcol + k * pitch;
+  const float2* wp = w2 + k;
+#pragma unroll 1
   for (int j = m0; j <= m1; ++j) {
-    const int k0 = seg_start[j], k1 = seg_start[j + 1];
+    const int n = seg_start[j + 1] - k;
+    k += n;
     float acc_dn = 0.0f, acc_up = 0.0f;
-    for (int k = k0; k < k1; ++k) {
-      const float p = ptile[k * ppitch + t];
-      const float2 w = w2[k];
-      acc_dn = fmaf(w.x, p, acc_dn);
-      acc_up = fmaf(w.y, p, acc_up);
+    int i = 0;
+#pragma unroll 1
+    for (; i + 2 <= n; i += 2) {
+      const float p0 = pp[0], p1 = pp[pitch];
+      const float2 wa = wp[0], wb = wp[1];
+      acc_dn = fmaf(wa.x, p0, acc_dn);
+      acc_up = fmaf(wa.y, p0, acc_up);
+      acc_dn = fmaf(wb.x, p1, acc_dn);
+      acc_up = fmaf(wb.y, p1, acc_up);
+      pp += 2 * pitch;
+      wp += 2;
+    }
+    if (i < n) {
+      const float p0 = pp[0];
+      const float2 wa = wp[0];
+      acc_dn = fmaf(wa.x, p0, acc_dn);
+      acc_up = fmaf(wa.y, p0, acc_up);
+      pp += pitch;
+      wp += 1;
     }
     if (j > m0) emit(j - 1, up_prev + acc_dn);
     up_prev = acc_up;

@@ -73,6 +73,7 @@ __device__ __forceinline__ void frame_sync() {
 
 constexpr int kThreads = 256;
 constexpr int kBox = 256;  // floats per TMA box (1 KB)
+constexpr int kMaxWorkers = 256;  // mel band groups per CTA: 8 warps * (32 / TF), TF >= 1
 
 // One thread queues the TMA boxes of a tile's PCM span.  Negative and
 // past-the-end sample coordinates are zero-filled by the TMA unit.
@@ -98,14 +99,15 @@ __global__ void __launch_bounds__(kThreads, 2)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 
   // ---- shared memory carve-up (mirrors stft_smem_bytes() on the host)
-  float* s_span = reinterpret_cast<float*>(smem_raw);                       // [2][span_alloc]
-  float* s_ptile = s_span + 2 * p.span_alloc;                               // [pt_bufs][F*ppitch]
+  float* s_span = reinterpret_cast<float*>(smem_raw);                       // [span_bufs][span_alloc]
+  float* s_ptile = s_span + p.span_bufs * p.span_alloc;                     // [pt_bufs][F*ppitch]
   float2* s_xb = reinterpret_cast<float2*>(s_ptile + ((p.pt_bufs * C::F * p.ppitch + 3) & ~3));  // [FPI][XBUF]
   float2* s_tw1 = s_xb + FPI * C::XBUF;                                     // [TW1]
   float2* s_tw2 = s_tw1 + C::TW1;                                           // [TW2]
   float2* s_w2 = s_tw2 + C::TW2;                                            // [F]
   int* s_seg = reinterpret_cast<int*>(s_w2 + C::F);                         // [n_mels + 2]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_seg + ((p.n_mels + 2 + 1) & ~1));  // [2]
+  int* s_mb = s_seg + ((p.n_mels + 2 + 1) & ~1);                            // [kMaxWorkers + 2] band-group bounds
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mb + kMaxWorkers + 2);    // [2]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   for (int i = tid; i < C::TW2; i += kThreads) s_tw2[i] = p.tw2[i];
   for (int i = tid; i < C::F; i += kThreads) s_w2[i] = p.w2[i];
   for (int i = tid; i < p.n_mels + 2; i += kThreads) s_seg[i] = p.seg_start[i];
+  for (int i = tid; i < kMaxWorkers + 1; i += kThreads) s_mb[i] = p.band_split[i];
 
   // Hann window of this thread's 16 complex points, pre-scaled by the 1/2 of the split step
   float2 wreg[16];
@@ -142,21 +145,22 @@ __global__ void __launch_bounds__(kThreads, 2)
   if (p.use_tma && tid == 0 && tile < n_tiles) issue_span<NFFT>(&tmap, p, tile, s_span, &s_bar[0]);
 
   for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int b = it & 1;
+    const int b = p.span_bufs == 2 ? (it & 1) : 0;
     const int clip = (int)(tile / p.tiles_per_clip);
     const int t0 = (int)(tile % p.tiles_per_clip) * p.TF;
     float* span = s_span + (size_t)b * p.span_alloc;
     // the span starts at the 16-byte aligned sample at or below the first needed one
     const int g_first = t0 * p.hop - NFFT / 2 - lead;
     const int shift = g_first - (g_first & ~3);
-    float* ptile = s_ptile + (size_t)(p.pt_bufs == 2 ? b : 0) * C::F * p.ppitch;
+    float* ptile = s_ptile + (size_t)(p.pt_bufs == 2 ? (it & 1) : 0) * C::F * p.ppitch;
 
     if (p.use_tma) {
-      // prefetch the next tile into the other buffer: its last readers finished
-      // before the __syncthreads that closed the previous tile's FFT phase
-      if (tid == 0 && tile + gridDim.x < n_tiles)
+      // two span buffers: prefetch the next tile into the other one now (its last readers
+      // finished before the __syncthreads that closed the previous tile's FFT phase);
+      // one span buffer: the prefetch is issued after this tile's FFT phase instead
+      if (p.span_bufs == 2 && tid == 0 && tile + gridDim.x < n_tiles)
         issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span + (size_t)(b ^ 1) * p.span_alloc, &s_bar[b ^ 1]);
-      mbar_wait(&s_bar[b], (uint32_t)(it >> 1) & 1u);
+      mbar_wait(&s_bar[b], (uint32_t)(p.span_bufs == 2 ? (it >> 1) : it) & 1u);
     } else {
       // plain coalesced loader (clip stride or base not 16-byte aligned)
       const long g0 = (long)(g_first & ~3);
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
     __syncthreads();  // power tile complete; span[b] no longer needed
+    if (p.use_tma && p.span_bufs == 1 && tid == 0 && tile + gridDim.x < n_tiles)
+      issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span, &s_bar[0]);  // streams in during the mel phase
 
     const int t_valid = min(p.TF, p.T - t0);
     if (p.power != nullptr) {
@@ -231,20 +237,27 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
     if (p.logmel != nullptr) {
-      // ---------------- mel phase: lane -> (frame, band group) ----------------
+      // ---------------- mel phase: lane -> frame, worker (warp or part of one) -> band group.
+      // Band groups are balanced on the host by bins + bands (c_api.cu: band_split).
       const int t = lane % p.TF;
       const int worker = (tid >> 5) * (32 / p.TF) + lane / p.TF;
-      const int m0 = worker * p.bands_per_worker;
-      const int m1 = min(p.n_mels, m0 + p.bands_per_worker);
+      const int m0 = s_mb[worker], m1 = s_mb[worker + 1];
       float mx = -FLT_MAX;
-      if (m0 < p.n_mels && t < t_valid) {
-        float* dst = p.logmel + (size_t)clip * p.n_mels * p.T + t0 + t;
+      if (m0 < m1 && t < t_valid) {
+        float* dst = p.logmel + ((size_t)clip * p.n_mels + m0) * p.T + t0 + t;
         const float amin = p.amin;
-        mel_column(ptile, p.ppitch, t, s_seg, s_w2, m0, m1, [&](int m, float val) {
-          const float db = 10.0f * log10f(fmaxf(amin, val));
-          dst[(size_t)m * p.T] = db;
+        const int T = p.T;
+        auto emit = [&](int, float val) {
+          // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is within 1e-6 dB here (x >= amin, never denormal)
+          const float db = 3.01029995663981195f * __log2f(fmaxf(amin, val));
+          *dst = db;
+          dst += T;
           mx = fmaxf(mx, db);
-        });
+        };
+        if (p.ppitch == 34)  // 32-frame tiles
+          mel_column<34>(ptile + t, 34, s_seg, s_w2, m0, m1, emit);
+        else
+          mel_column<0>(ptile + t, p.ppitch, s_seg, s_w2, m0, m1, emit);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -262,15 +275,16 @@ __global__ void __launch_bounds__(kThreads, 2)
 // ---------------------------------------------------------------------------
 
 template <int NFFT>
-static size_t smem_bytes_t(int span_alloc, int ppitch, int pt_bufs, int n_mels) {
+static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_bufs, int n_mels) {
   using C = FftCfg<NFFT>;
   constexpr int FPI = kThreads / C::TPF;
   size_t b = 0;
-  b += (size_t)2 * span_alloc * 4;
+  b += (size_t)span_bufs * span_alloc * 4;
   b += (size_t)((pt_bufs * C::F * ppitch + 3) & ~3) * 4;
   b += (size_t)FPI * C::XBUF * 8;
   b += (size_t)(C::TW1 + C::TW2 + C::F) * 8;
   b += (size_t)((n_mels + 2 + 1) & ~1) * 4;
+  b += (size_t)(kMaxWorkers + 2) * 4;
   b += 16;
   return b;
 }
@@ -297,13 +311,13 @@ int stft_geometry(int n_fft, StftGeometry* g) {
   }
 }
 
-size_t stft_smem_bytes(int n_fft, int span_alloc, int ppitch, int pt_bufs, int n_mels) {
+size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int n_mels) {
   switch (n_fft) {
-    case 256: return smem_bytes_t<256>(span_alloc, ppitch, pt_bufs, n_mels);
-    case 512: return smem_bytes_t<512>(span_alloc, ppitch, pt_bufs, n_mels);
-    case 1024: return smem_bytes_t<1024>(span_alloc, ppitch, pt_bufs, n_mels);
-    case 2048: return smem_bytes_t<2048>(span_alloc, ppitch, pt_bufs, n_mels);
-    case 4096: return smem_bytes_t<4096>(span_alloc, ppitch, pt_bufs, n_mels);
+    case 256: return smem_bytes_t<256>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
+    case 512: return smem_bytes_t<512>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
+    case 1024: return smem_bytes_t<1024>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
+    case 2048: return smem_bytes_t<2048>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
+    case 4096: return smem_bytes_t<4096>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
     default: return 0;
   }
 }

@@ -103,8 +103,12 @@ extern "C" int emu_mel(const float* power, long T, int F, const int* seg_start, 
     for (int k = 0; k < F; ++k) col[k] = power[(long)k * T + t];
     for (int m0 = 0; m0 < n_mels; m0 += bands_per_worker) {
       int m1 = m0 + bands_per_worker < n_mels ? m0 + bands_per_worker : n_mels;
-      mel_column(col.data(), 1, 0, seg_start, reinterpret_cast<const float2*>(w2), m0, m1,
-                 [&](int m, float v) { mel_out[(long)m * T + t] = v; });
+      if ((m0 / bands_per_worker) & 1)
+        mel_column<1>(col.data(), 1, seg_start, reinterpret_cast<const float2*>(w2), m0, m1,
+                      [&](int m, float v) { mel_out[(long)m * T + t] = v; });
+      else
+        mel_column<0>(col.data(), 1, seg_start, reinterpret_cast<const float2*>(w2), m0, m1,
+                      [&](int m, float v) { mel_out[(long)m * T + t] = v; });
     }
   }
   return 0;
