@@ -206,7 +206,7 @@ def run_b200(args):
             dist.barrier()
 
     lib = mm.lib()
-    fx = mm.FeatureExtractor(SR, device=local, **PARAMS)
+    fx = mm.FeatureExtractor(SR, device=local, flags=int(os.environ.get("MMF_FLAGS", "0")), **PARAMS)
     plan, prm = fx.plan, fx.prm
     pcm = mm.synth_batch_device(CLIPS, N_SAMPLES, SR, seed=1234 + rank, device=dev)
     T = plan.num_frames(N_SAMPLES)

@@ -49,6 +49,8 @@ MMF_ERR_NOMEM = -5
 MMF_FLAG_NO_TMA = 1
 MMF_FLAG_SPLIT_SMEM = 2
 MMF_FLAG_UNFUSED_CHANGE = 4
+MMF_FLAG_SCALAR_FFT = 8
+MMF_FLAG_MMA_MEL = 16
 
 
 class mmf_config(C.Structure):

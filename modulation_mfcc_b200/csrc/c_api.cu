@@ -239,70 +239,9 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   p->cfg = *cfg;
   p->F = cfg->n_fft / 2 + 1;
   p->sm_count = prop.multiProcessorCount;
-  stft_geometry(cfg->n_fft, &p->geo);
+  p->packed = (stft_packed_supported(cfg->n_fft) && !(cfg->flags & MMF_FLAG_SCALAR_FFT)) ? 1 : 0;
+  stft_geometry(cfg->n_fft, p->packed, &p->geo);
   p->lead = cfg->preemph != 0.0f ? 2 : 0;
-
-  // ---- tile geometry: largest TF (multiple of frames/iteration, power of two <= 32)
-  // whose shared memory lets two CTAs share an SM; otherwise the smallest TF.
-  const int fpi = p->geo.fpi;
-  const int fpw = p->geo.tpf < 32 ? 32 / p->geo.tpf : 1;  // frames per warp in the FFT phase
-  auto pitch_for = [&](int tf) {
-    int pp = std::max(tf, fpw);
-    if (fpw == 1) {
-      if ((pp & 1) == 0) ++pp;
-    } else {
-      pp = (pp + fpw - 1) / fpw * fpw;
-      if (((pp / fpw) & 1) == 0) pp += fpw;
-    }
-    return pp;
-  };
-  auto smem_for = [&](int tf, int span_bufs, int pt_bufs) {
-    const int span = (tf - 1) * cfg->hop_length + cfg->n_fft + p->lead + 3;
-    const int alloc = (span + 255) / 256 * 256;
-    return stft_smem_bytes(cfg->n_fft, alloc, span_bufs, pitch_for(tf), pt_bufs, cfg->n_mels);
-  };
-  // Preference: the widest tile first (32 frames = one frame per lane in the mel phase, no
-  // divergence between band groups), then as much double buffering as two CTAs per SM allow
-  // (<= 113 KB each: 227 KB per SM, 1 KB reserved per CTA); one CTA per SM as the last resort.
-  const size_t budget2 = 113 * 1024, budget1 = 226 * 1024;
-  static const int kBufChoices[4][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}};  // {span_bufs, pt_bufs}
-  int tf = 0, pt_bufs = 2, span_bufs = 2, ctas = 2;
-  auto pick = [&](size_t budget) {
-    for (int cand = 32; cand >= 1 && tf == 0; cand >>= 1) {
-      if (cand < fpi || cand % fpi) continue;
-      for (const auto& ch : kBufChoices)
-        if (smem_for(cand, ch[0], ch[1]) <= budget) {
-          tf = cand;
-          span_bufs = ch[0];
-          pt_bufs = ch[1];
-          break;
-        }
-    }
-  };
-  pick(budget2);
-  if (tf == 0) {
-    ctas = 1;
-    pick(budget1);
-  }
-  // debugging / tuning overrides
-  if (const char* e = std::getenv("MMF_TF")) {
-    const int v = std::atoi(e);
-    if (v >= fpi && v <= 32 && (v & (v - 1)) == 0 && v % fpi == 0) tf = v;
-    if (const char* e2 = std::getenv("MMF_SPAN_BUFS")) span_bufs = std::atoi(e2) == 1 ? 1 : 2;
-    if (const char* e3 = std::getenv("MMF_PT_BUFS")) pt_bufs = std::atoi(e3) == 1 ? 1 : 2;
-    ctas = smem_for(tf, span_bufs, pt_bufs) <= budget2 ? 2 : 1;
-    if (smem_for(tf, span_bufs, pt_bufs) > budget1) tf = 0;
-  }
-  if (tf == 0 || fpi > 32) {
-    delete p;
-    return fail(MMF_ERR_UNSUPPORTED, "hop_length/n_fft combination needs more shared memory than one SM has");
-  }
-  p->TF = tf;
-  p->pt_bufs = pt_bufs;
-  p->span_bufs = span_bufs;
-  p->ctas_per_sm = ctas;
-  p->ppitch = pitch_for(tf);
-  p->smem = smem_for(tf, span_bufs, pt_bufs);
 
   // ---- constant tables
   std::vector<float> window, mel, dct;
@@ -315,9 +254,153 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     return fail(MMF_ERR_UNSUPPORTED, "mel filterbank is not a two-slope (triangular) bank");
   }
   host_dct(cfg->n_mfcc, cfg->n_mels, dct);
-  // ---- mel band groups: 8 warps * (32 / TF) workers, contiguous bands each, balanced on
-  // cost = bins walked + bands emitted (smallest achievable maximum, greedy fill under a
-  // binary-searched bound)
+
+  // ---- tensor-core mel tables: the (n-tile of 8 bands, k-tile of 8 bins) blocks of the filterbank
+  // that are not all zero, n-major; per block the B fragments of mma.m16n8k8
+  // (b0: k = lane%4, b1: k = lane%4 + 4; n = lane/4) as plain fp32 (split into TF32 hi/lo on the fly)
+  const int NT = (cfg->n_mels + 7) / 8;
+  std::vector<float2> mma_bw;
+  std::vector<int> mma_pk8, mma_npair(NT + 1, 0);
+  {
+    const int F = p->F;
+    auto wgt = [&](int k, int band) -> float {
+      return (k < F && band < cfg->n_mels) ? mel[(size_t)band * F + k] : 0.0f;
+    };
+    for (int n = 0; n < NT; ++n) {
+      mma_npair[n] = (int)mma_pk8.size();
+      for (int k8 = 0; k8 < (F + 7) / 8; ++k8) {
+        bool any = false;
+        for (int k = 8 * k8; k < 8 * k8 + 8 && !any; ++k)
+          for (int b = 8 * n; b < 8 * n + 8 && !any; ++b) any = wgt(k, b) != 0.0f;
+        if (!any) continue;
+        mma_pk8.push_back(k8);
+        for (int lane = 0; lane < 32; ++lane) {
+          const int g = lane >> 2, t4 = lane & 3;
+          mma_bw.push_back(make_float2(wgt(8 * k8 + t4, 8 * n + g), wgt(8 * k8 + t4 + 4, 8 * n + g)));
+        }
+      }
+    }
+    mma_npair[NT] = (int)mma_pk8.size();
+  }
+  p->mma_n_pairs = (int)mma_pk8.size();
+
+  // ---- tile geometry.  Preference: the widest tile first (32 frames = one frame per lane /
+  // two MMA row tiles in the mel phase), then as much double buffering as two CTAs per SM allow
+  // (<= 113 KB each: 227 KB per SM, 1 KB reserved per CTA); one CTA per SM as the last resort.
+  const int fpi = p->geo.fpi;
+  const int fpw = p->geo.tpf < 32 ? 32 / p->geo.tpf : 1;  // frames per warp in the FFT phase
+  auto pitch_for = [&](int tf) {
+    if (p->packed) {
+      // two-frame path: 64-bit stores of (frame, frame+1) pairs by consecutive bins:
+      // pitch == 2 (mod 4) keeps them 8-byte aligned and conflict-free per half-warp
+      int pp = std::max(tf, 2);
+      while (pp % 4 != 2) ++pp;
+      return pp;
+    }
+    int pp = std::max(tf, fpw);
+    if (fpw == 1) {
+      if ((pp & 1) == 0) ++pp;
+    } else {
+      pp = (pp + fpw - 1) / fpw * fpw;
+      if (((pp / fpw) & 1) == 0) pp += fpw;
+    }
+    return pp;
+  };
+  const size_t budget2 = 113 * 1024, budget1 = 226 * 1024;
+  static const int kBufChoices[4][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}};  // {span_bufs, pt_bufs}
+  struct Geo {
+    int tf = 0, span_bufs = 2, pt_bufs = 2, ctas = 2;
+    size_t smem = 0;
+  };
+  auto smem_for = [&](int tf, int span_bufs, int pt_bufs, int mel_mma) {
+    const int span = (tf - 1) * cfg->hop_length + cfg->n_fft + p->lead + 3;
+    const int alloc = (span + 255) / 256 * 256;
+    return stft_smem_bytes(cfg->n_fft, alloc, span_bufs, pitch_for(tf), pt_bufs, p->packed,
+                           stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, mel_mma, p->mma_n_pairs));
+  };
+  auto choose = [&](int mel_mma) {
+    Geo g;
+    for (int pass = 0; pass < 2 && g.tf == 0; ++pass) {
+      const size_t budget = pass == 0 ? budget2 : budget1;
+      g.ctas = pass == 0 ? 2 : 1;
+      for (int cand = 32; cand >= 1 && g.tf == 0; cand >>= 1) {
+        if (cand < fpi || cand % fpi) continue;
+        for (const auto& ch : kBufChoices) {
+          const size_t b = smem_for(cand, ch[0], ch[1], mel_mma);
+          if (b <= budget) {
+            g.tf = cand;
+            g.span_bufs = ch[0];
+            g.pt_bufs = ch[1];
+            g.smem = b;
+            break;
+          }
+        }
+      }
+    }
+    return g;
+  };
+  // The tensor-core mel (MMF_FLAG_MMA_MEL) keeps its B fragments in shared memory: honoured unless
+  // that costs tile width or the second CTA per SM (very wide filterbanks).  Default is the sparse
+  // FP32 walk: the filterbank is 95-98 % zeros and the split-precision MMA path measured 3-7 %
+  // slower on every BASELINE shape.
+  Geo gs = choose(0), gm = choose(1);
+  const bool units_fit = NT * 2 <= 8 * 16;
+  p->mel_mma = ((cfg->flags & MMF_FLAG_MMA_MEL) && units_fit && gm.tf != 0 && gm.tf >= gs.tf &&
+                gm.ctas >= gs.ctas)
+                   ? 1
+                   : 0;
+  Geo g = p->mel_mma ? gm : gs;
+  // debugging / tuning overrides
+  if (const char* e = std::getenv("MMF_TF")) {
+    const int v = std::atoi(e);
+    if (v >= fpi && v <= 32 && (v & (v - 1)) == 0 && v % fpi == 0) g.tf = v;
+    if (const char* e2 = std::getenv("MMF_SPAN_BUFS")) g.span_bufs = std::atoi(e2) == 1 ? 1 : 2;
+    if (const char* e3 = std::getenv("MMF_PT_BUFS")) g.pt_bufs = std::atoi(e3) == 1 ? 1 : 2;
+    g.smem = smem_for(g.tf, g.span_bufs, g.pt_bufs, p->mel_mma);
+    g.ctas = g.smem <= budget2 ? 2 : 1;
+    if (g.smem > budget1) g.tf = 0;
+  }
+  if (g.tf == 0 || fpi > 32) {
+    delete p;
+    return fail(MMF_ERR_UNSUPPORTED, "hop_length/n_fft combination needs more shared memory than one SM has");
+  }
+  const int tf = g.tf;
+  p->TF = tf;
+  p->pt_bufs = g.pt_bufs;
+  p->span_bufs = g.span_bufs;
+  p->ctas_per_sm = g.ctas;
+  p->ppitch = pitch_for(tf);
+  p->smem = g.smem;
+  p->mel_tab_bytes = stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, p->mel_mma, p->mma_n_pairs);
+
+  // ---- tensor-core mel work list: unit = (n-tile, 16-frame m-tile), cost = blocks of the n-tile;
+  // longest-processing-time assignment to the 8 warps (each unit is produced by exactly one warp)
+  std::vector<int> mma_units(8 * 16, -1);
+  if (p->mel_mma) {
+    const int MT = (tf + 15) / 16;
+    std::vector<std::pair<int, int>> units;  // (cost, n | m << 8)
+    for (int n = 0; n < NT; ++n)
+      for (int m = 0; m < MT; ++m) units.push_back({mma_npair[n + 1] - mma_npair[n], n | (m << 8)});
+    std::stable_sort(units.begin(), units.end(),
+                     [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+    long load[8] = {0};
+    int cnt[8] = {0};
+    for (const auto& u : units) {
+      int w = 0;
+      for (int i = 1; i < 8; ++i)
+        if (load[i] < load[w] || (load[i] == load[w] && cnt[i] < cnt[w])) w = i;
+      if (cnt[w] >= 16) {  // cannot happen with units_fit, kept as a guard
+        delete p;
+        return fail(MMF_ERR_UNSUPPORTED, "too many mel tiles per warp");
+      }
+      mma_units[w * 16 + cnt[w]++] = u.second;
+      load[w] += u.first + 2;  // + epilogue
+    }
+  }
+
+  // ---- mel band groups of the sparse FP32 walk: 8 warps * (32 / TF) workers, contiguous bands
+  // each, balanced on cost = bins walked + bands emitted (smallest achievable maximum, greedy
+  // fill under a binary-searched bound)
   std::vector<int> band_split(257, cfg->n_mels);
   {
     const int workers = std::min(256, 8 * (32 / tf));
@@ -360,6 +443,9 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   if ((e = upload(&p->d_window, window)) != cudaSuccess || (e = upload(&p->d_tw1, tw1)) != cudaSuccess ||
       (e = upload(&p->d_tw2, tw2)) != cudaSuccess || (e = upload(&p->d_seg, sp.seg_start)) != cudaSuccess ||
       (e = upload(&p->d_band_split, band_split)) != cudaSuccess ||
+      (e = upload(&p->d_mma_bw, mma_bw)) != cudaSuccess || (e = upload(&p->d_mma_pk8, mma_pk8)) != cudaSuccess ||
+      (e = upload(&p->d_mma_npair, mma_npair)) != cudaSuccess ||
+      (e = upload(&p->d_mma_units, mma_units)) != cudaSuccess ||
       (e = upload(&p->d_w2, w2)) != cudaSuccess || (e = upload(&p->d_dct, dct_pad)) != cudaSuccess) {
     mmf_plan_destroy(p);
     return cuda_fail(e, "uploading plan constants");
@@ -385,6 +471,10 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_tw2);
   cudaFree(p->d_seg);
   cudaFree(p->d_band_split);
+  cudaFree(p->d_mma_bw);
+  cudaFree(p->d_mma_pk8);
+  cudaFree(p->d_mma_npair);
+  cudaFree(p->d_mma_units);
   cudaFree(p->d_w2);
   cudaFree(p->d_dct);
   cudaFree(p->ws);
@@ -435,6 +525,18 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   a.span_alloc = (a.span_floats + 255) / 256 * 256;
   a.ppitch = p->ppitch;
   a.pt_bufs = p->pt_bufs;
+  a.packed = p->packed;
+  a.mel_mma = p->mel_mma;
+  a.m_tiles = (p->TF + 15) / 16;
+  a.mma_n_pairs = p->mma_n_pairs;
+  a.mel_tab_bytes = (int)p->mel_tab_bytes;
+  a.mma_bw = p->d_mma_bw;
+  a.mma_pk8 = p->d_mma_pk8;
+  a.mma_npair = p->d_mma_npair;
+  a.mma_units = p->d_mma_units;
+  if (const char* e = std::getenv("MMF_DEBUG_SKIP")) a.debug_skip = std::atoi(e);
+  a.early_tma = 1;
+  if (const char* e = std::getenv("MMF_EARLY_TMA")) a.early_tma = std::atoi(e);
   a.span_bufs = p->span_bufs;
   a.vec_ok = (c.hop_length % 2 == 0) ? 1 : 0;
   a.split_regs = (c.n_fft == 512 && !(c.flags & MMF_FLAG_SPLIT_SMEM)) ? 1 : 0;

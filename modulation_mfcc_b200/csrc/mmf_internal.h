@@ -32,6 +32,17 @@ struct StftArgs {
   int use_tma;
   int vec_ok;            // 64-bit shared loads allowed (hop even)
   int split_regs;        // n_fft = 512: shuffle-based split step
+  int mel_mma;           // mel projection on the tensor cores (mma.sync TF32 x3) instead of the sparse FP32 walk
+  int m_tiles;           // 16-frame MMA row tiles per tile of TF frames (1 or 2)
+  int mma_n_pairs;       // non-zero (n-tile, k-tile) blocks of the filterbank
+  int mel_tab_bytes;     // shared-memory bytes of the mel tables of the active mode
+  const float2* mma_bw;  // [n_pairs][32] B fragments: W[8*k8 + lane%4 (+4)][8*n + lane/4], n-major
+  const int* mma_pk8;    // [n_pairs] k-tile of each block
+  const int* mma_npair;  // [NT + 1] block range of each 8-band n-tile
+  const int* mma_units;  // [8][16] (n | m << 8) units of each warp, -1 terminated
+  int early_tma;         // single span buffer: prefetch the next tile right after the load phase (extra barrier)
+  int debug_skip;        // profiling aid (MMF_DEBUG_SKIP): bit 0 skips the FFT phase, bit 1 the mel phase
+  int packed;            // two frames per thread group on packed FP32 instructions (FFMA2/FADD2)
   int n_mels;
   float amin;
   float preemph;
@@ -50,8 +61,11 @@ struct StftGeometry {
   int tpf, fpi, tw1, tw2, r3, m;
 };
 
-int stft_geometry(int n_fft, StftGeometry* g);
-size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int n_mels);
+bool stft_packed_supported(int n_fft);
+int stft_geometry(int n_fft, int packed, StftGeometry* g);
+size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs);
+size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed,
+                       size_t mel_tab_bytes);
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
                             cudaStream_t st);
 
@@ -122,7 +136,7 @@ struct mmf_plan {
   int sm_count;
   mmf::StftGeometry geo;
   // tile geometry
-  int TF, ppitch, pt_bufs, span_bufs, ctas_per_sm, lead;
+  int TF, ppitch, pt_bufs, span_bufs, ctas_per_sm, lead, packed, mel_mma;
   size_t smem;
   // device constants
   float* d_window = nullptr;
@@ -130,6 +144,12 @@ struct mmf_plan {
   float2* d_tw2 = nullptr;
   int* d_seg = nullptr;
   int* d_band_split = nullptr;
+  float2* d_mma_bw = nullptr;
+  int* d_mma_pk8 = nullptr;
+  int* d_mma_npair = nullptr;
+  int* d_mma_units = nullptr;
+  int mma_n_pairs = 0;
+  size_t mel_tab_bytes = 0;
   float2* d_w2 = nullptr;
   float* d_dct = nullptr;  // [n_mels][nc_pad]
   int nc_pad = 0;

@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(kModThreads)
     // power of this thread's bins -> registers, then (once every thread of the slot
     // has read its Z pairs) into shared memory in natural order, so that the
     // magnitude store and the band sums walk contiguous bins
-    float pk[17];
+    float pwr[17];
     {
       int q = 0;
-      ph_split_smem_cb<NFFT>(xb, tau, wtau, [&](int, float p) { pk[q++] = p; });
+      ph_split_smem_cb<NFFT>(xb, tau, wtau, [&](int, float p) { pwr[q++] = p; });
     }
     __syncwarp();
     float* pw = reinterpret_cast<float*>(xb);  // [nb] floats, aliases the exchange buffer
@@ -113,10 +113,10 @@ __global__ void __launch_bounds__(kModThreads)
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int k = tau + C::TPF * r;
-        pw[k] = pk[q++];
-        pw[C::M - k] = pk[q++];
+        pw[k] = pwr[q++];
+        pw[C::M - k] = pwr[q++];
       }
-      if (tau == 0) pw[C::M / 2] = pk[16];
+      if (tau == 0) pw[C::M / 2] = pwr[16];
     }
     __syncwarp();
     if (mag != nullptr && valid) {

@@ -15,6 +15,11 @@
 //   pass 3: R3-pt DFT over m1 -> j1
 //   k  = 16*(R2*j1 + j2) + k2
 //
+// Every phase is generic over the complex value type (fft_regs.cuh): float2 = one
+// frame per thread, c2 = two adjacent frames per thread on packed FP32
+// instructions.  The exchange buffer holds 8 bytes per element either way (the
+// two-frame path exchanges real and imaginary parts in two rounds).
+//
 // Every phase is __host__ __device__: tests/emu/ runs the same code thread by
 // thread on the CPU against numpy's rfft, so the index algebra is checked
 // without a GPU.
@@ -52,13 +57,38 @@ MMF_HD float2 w32(int r) {
   return make_float2(c[r], -c[8 - r]);
 }
 
+// component access for the exchanges.  PART 0: the whole value (float2 path, one
+// round); PART 1 / 2: the real / imaginary pk of a two-frame value (two rounds
+// through the same 8-byte-per-element buffer).
+template <int PART>
+MMF_HD float2 xget(const float2& v) {
+  return v;
+}
+template <int PART>
+MMF_HD void xset(float2& v, float2 e) {
+  v = e;
+}
+template <int PART>
+MMF_HD pk xget(const c2& v) {
+  return PART == 1 ? v.x : v.y;
+}
+template <int PART>
+MMF_HD void xset(c2& v, pk e) {
+  if (PART == 1) {
+    v.x = e;
+  } else {
+    v.y = e;
+  }
+}
+
 // ---- phase L: gather 16 strided complex points of the frame and apply the window
 // span: PCM of the tile in shared memory; frame starts at span[frame_off].
 // wreg[n2] = 0.5 * (w[2c], w[2c+1]) with c = tau + TPF*n2 (the 0.5 is the 1/2 of
 // the real-FFT split step, folded in exactly).
 template <int NFFT, bool VEC>
-MMF_HD void ph_load(float2 (&v)[16], const float* span, int frame_off, int tau, const float2 (&wreg)[16]) {
+MMF_HD void ph_load(float2 (&v)[16], const float* span, int frame_off, int hop, int tau, const float2 (&wreg)[16]) {
   using C = FftCfg<NFFT>;
+  (void)hop;
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) {
     const int c = tau + C::TPF * n2;
@@ -73,30 +103,71 @@ MMF_HD void ph_load(float2 (&v)[16], const float* span, int frame_off, int tau, 
   }
 }
 
+// Two frames (frame_off and frame_off + hop): the window multiply runs on the
+// (re, im) pairs as loaded (one packed multiply per frame and point), then the
+// halves are regrouped into (A.re, B.re), (A.im, B.im).
+template <int NFFT, bool VEC>
+MMF_HD void ph_load(c2 (&v)[16], const float* span, int frame_off, int hop, int tau, const float2 (&wreg)[16]) {
+  using C = FftCfg<NFFT>;
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int c = tau + C::TPF * n2;
+    float2 a, b;
+    if constexpr (VEC) {
+      a = *reinterpret_cast<const float2*>(span + frame_off + 2 * c);
+      b = *reinterpret_cast<const float2*>(span + frame_off + hop + 2 * c);
+    } else {
+      a.x = span[frame_off + 2 * c];
+      a.y = span[frame_off + 2 * c + 1];
+      b.x = span[frame_off + hop + 2 * c];
+      b.y = span[frame_off + hop + 2 * c + 1];
+    }
+    const pk w = pmake(wreg[n2].x, wreg[n2].y);
+    const pk pa = smul(pmake(a.x, a.y), w), pb = smul(pmake(b.x, b.y), w);
+    v[n2] = CxTraits<c2>::make(pmake(plo(pa), plo(pb)), pmake(phi(pa), phi(pb)));
+  }
+}
+
 // Same with first-order pre-emphasis y'[n] = y[n] - a*y[n-1] applied to the
 // un-padded signal (y[-1] = 0) before the zero centre padding: n_valid is the
 // number of samples from the frame start to the end of the clip, so samples at
 // or beyond it stay exactly zero.  Needs one sample of history before the frame
 // (the span is loaded with lead >= 1).
+MMF_HD float2 pre_point(const float* span, int i0_abs, int i0, float a, long n_valid, float2 w) {
+  const float xm = span[i0_abs - 1];
+  const float x0 = span[i0_abs];
+  const float x1 = span[i0_abs + 1];
+  const float y0 = (i0 < n_valid) ? x0 - a * xm : 0.0f;
+  const float y1 = (i0 + 1 < n_valid) ? x1 - a * x0 : 0.0f;
+  return make_float2(y0 * w.x, y1 * w.y);
+}
 template <int NFFT>
-MMF_HD void ph_load_pre(float2 (&v)[16], const float* span, int frame_off, int tau, const float2 (&wreg)[16], float a,
-                        long n_valid) {
+MMF_HD void ph_load_pre(float2 (&v)[16], const float* span, int frame_off, int hop, int tau, const float2 (&wreg)[16],
+                        float a, long n_valid) {
+  using C = FftCfg<NFFT>;
+  (void)hop;
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int i0 = 2 * (tau + C::TPF * n2);
+    v[n2] = pre_point(span, frame_off + i0, i0, a, n_valid, wreg[n2]);
+  }
+}
+template <int NFFT>
+MMF_HD void ph_load_pre(c2 (&v)[16], const float* span, int frame_off, int hop, int tau, const float2 (&wreg)[16],
+                        float a, long n_valid) {
   using C = FftCfg<NFFT>;
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) {
     const int i0 = 2 * (tau + C::TPF * n2);
-    const float xm = span[frame_off + i0 - 1];
-    const float x0 = span[frame_off + i0];
-    const float x1 = span[frame_off + i0 + 1];
-    const float y0 = (i0 < n_valid) ? x0 - a * xm : 0.0f;
-    const float y1 = (i0 + 1 < n_valid) ? x1 - a * x0 : 0.0f;
-    v[n2] = make_float2(y0 * wreg[n2].x, y1 * wreg[n2].y);
+    const float2 fa = pre_point(span, frame_off + i0, i0, a, n_valid, wreg[n2]);
+    const float2 fb = pre_point(span, frame_off + hop + i0, i0, a, n_valid - hop, wreg[n2]);
+    v[n2] = CxTraits<c2>::make(pmake(fa.x, fb.x), pmake(fa.y, fb.y));
   }
 }
 
 // ---- pass 1: 16-point DFT over n2 and the W_M^{n1*k2} twiddle
-template <int NFFT>
-MMF_HD void ph_pass1(float2 (&v)[16], const float2* tw1, int tau) {
+template <int NFFT, typename V>
+MMF_HD void ph_pass1(V (&v)[16], const typename CxTraits<V>::Tw* tw1, int tau) {
   using C = FftCfg<NFFT>;
   dft16(v);
 #pragma unroll
@@ -104,28 +175,28 @@ MMF_HD void ph_pass1(float2 (&v)[16], const float2* tw1, int tau) {
 }
 
 // ---- exchange 1: A'[n1][k2] at xb[k2*PITCH1 + n1]
-template <int NFFT>
-MMF_HD void ph_x1_write(const float2 (&v)[16], float2* xb, int tau) {
+template <int NFFT, int PART = 0, typename V>
+MMF_HD void ph_x1_write(const V (&v)[16], typename CxTraits<V>::Xe* xb, int tau) {
   using C = FftCfg<NFFT>;
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) xb[k2 * C::PITCH1 + tau] = v[k2];
+  for (int k2 = 0; k2 < 16; ++k2) xb[k2 * C::PITCH1 + tau] = xget<PART>(v[k2]);
 }
 
 // thread tau' = m1 + R3*kq reads n1 = m1 + R3*m2, k2 = kq + R2*u into v[u*R2 + m2]
-template <int NFFT>
-MMF_HD void ph_x1_read(float2 (&v)[16], const float2* xb, int tau) {
+template <int NFFT, int PART = 0, typename V>
+MMF_HD void ph_x1_read(V (&v)[16], const typename CxTraits<V>::Xe* xb, int tau) {
   using C = FftCfg<NFFT>;
   const int m1 = tau % C::R3, kq = tau / C::R3;
 #pragma unroll
   for (int u = 0; u < C::NB2; ++u)
 #pragma unroll
     for (int m2 = 0; m2 < C::R2; ++m2)
-      v[u * C::R2 + m2] = xb[(kq + C::R2 * u) * C::PITCH1 + m1 + C::R3 * m2];
+      xset<PART>(v[u * C::R2 + m2], xb[(kq + C::R2 * u) * C::PITCH1 + m1 + C::R3 * m2]);
 }
 
 // ---- pass 2: NB2 butterflies of radix R2 over m2 -> j2, twiddle W_TPF^{m1*j2}
-template <int NFFT>
-MMF_HD void ph_pass2(float2 (&v)[16], const float2* tw2, int tau) {
+template <int NFFT, typename V>
+MMF_HD void ph_pass2(V (&v)[16], const typename CxTraits<V>::Tw* tw2, int tau) {
   using C = FftCfg<NFFT>;
   dft_groups<C::R2, C::NB2>(v);
   if constexpr (C::R3 > 1) {
@@ -137,35 +208,35 @@ MMF_HD void ph_pass2(float2 (&v)[16], const float2* tw2, int tau) {
 
 // ---- exchange 2 (R3 > 1 only; R2 == 16, u == 0, kq == k2):
 // B'[m1][j2][k2] at xb[(j2*R3 + m1)*PITCH2 + k2]
-template <int NFFT>
-MMF_HD void ph_x2_write(const float2 (&v)[16], float2* xb, int tau) {
+template <int NFFT, int PART = 0, typename V>
+MMF_HD void ph_x2_write(const V (&v)[16], typename CxTraits<V>::Xe* xb, int tau) {
   using C = FftCfg<NFFT>;
   const int m1 = tau % C::R3, k2 = tau / C::R3;
 #pragma unroll
-  for (int j2 = 0; j2 < 16; ++j2) xb[(j2 * C::R3 + m1) * C::PITCH2 + k2] = v[j2];
+  for (int j2 = 0; j2 < 16; ++j2) xb[(j2 * C::R3 + m1) * C::PITCH2 + k2] = xget<PART>(v[j2]);
 }
 
 // thread tau'' = k2 + 16*jq reads j2 = jq + R3*e, all m1, into v[e*R3 + m1]
-template <int NFFT>
-MMF_HD void ph_x2_read(float2 (&v)[16], const float2* xb, int tau) {
+template <int NFFT, int PART = 0, typename V>
+MMF_HD void ph_x2_read(V (&v)[16], const typename CxTraits<V>::Xe* xb, int tau) {
   using C = FftCfg<NFFT>;
   const int k2 = tau % 16, jq = tau / 16;
 #pragma unroll
   for (int e = 0; e < C::NB3; ++e)
 #pragma unroll
     for (int m1 = 0; m1 < C::R3; ++m1)
-      v[e * C::R3 + m1] = xb[((jq + C::R3 * e) * C::R3 + m1) * C::PITCH2 + k2];
+      xset<PART>(v[e * C::R3 + m1], xb[((jq + C::R3 * e) * C::R3 + m1) * C::PITCH2 + k2]);
 }
 
-template <int NFFT>
-MMF_HD void ph_pass3(float2 (&v)[16]) {
+template <int NFFT, typename V>
+MMF_HD void ph_pass3(V (&v)[16]) {
   using C = FftCfg<NFFT>;
   dft_groups<C::R3, C::NB3>(v);
 }
 
 // ---- natural-order store of Z for the split step: z[k], k = 16*(R2*j1 + j2) + k2
-template <int NFFT>
-MMF_HD void ph_z_write(const float2 (&v)[16], float2* xb, int tau) {
+template <int NFFT, int PART = 0, typename V>
+MMF_HD void ph_z_write(const V (&v)[16], typename CxTraits<V>::Xe* xb, int tau) {
   using C = FftCfg<NFFT>;
   if constexpr (C::R3 > 1) {
     const int k2 = tau % 16, jq = tau / 16;
@@ -174,48 +245,74 @@ MMF_HD void ph_z_write(const float2 (&v)[16], float2* xb, int tau) {
 #pragma unroll
       for (int j1 = 0; j1 < C::R3; ++j1) {
         const int j2 = jq + C::R3 * e;
-        xb[16 * (C::R2 * j1 + j2) + k2] = v[e * C::R3 + j1];
+        xb[16 * (C::R2 * j1 + j2) + k2] = xget<PART>(v[e * C::R3 + j1]);
       }
   } else {
     const int kq = tau;  // m1 == 0
 #pragma unroll
     for (int u = 0; u < C::NB2; ++u)
 #pragma unroll
-      for (int j2 = 0; j2 < C::R2; ++j2) xb[16 * j2 + kq + C::R2 * u] = v[u * C::R2 + j2];
+      for (int j2 = 0; j2 < C::R2; ++j2) xb[16 * j2 + kq + C::R2 * u] = xget<PART>(v[u * C::R2 + j2]);
   }
 }
 
-// ---- split step for one conjugate pair: a = Z[k], b = Z[(M-k) mod M] (both
-// already scaled by 1/2 through the window).  Returns (|X[k]|^2, |X[M-k]|^2).
-// wk = e^{-2*pi*i*k/NFFT} is applied as c32[r] (compile-time) then wtau.
-MMF_HD float2 split_pair(float2 a, float2 b, float2 c32r, float2 wtau) {
-  const float2 E = make_float2(a.x + b.x, a.y - b.y);
-  const float2 O = make_float2(a.y + b.y, b.x - a.x);
-  const float2 WO = cmul(cmul(O, c32r), wtau);
-  const float2 Xp = cadd(E, WO), Xm = csub(E, WO);
-  return make_float2(Xp.x * Xp.x + Xp.y * Xp.y, Xm.x * Xm.x + Xm.y * Xm.y);
-}
-
-// ---- split step from the natural-order buffer (any NFFT).
-// Thread tau handles k = tau + TPF*r, r = 0..7 (covers [0, M/2)); tau == 0 also k = M/2.
-// Power lands in ptile[k*ppitch + t].
-template <int NFFT>
-MMF_HD void ph_split_smem(const float2* xb, float* ptile, int ppitch, int t, int tau, float2 wtau) {
+// gather of the conjugate pairs this thread splits: a[r] = Z[k], b[r] = Z[(M-k) mod M]
+// for k = tau + TPF*r, r = 0..7, and a[8] = Z[M/2] (used by tau == 0 only)
+template <int NFFT, int PART = 0, typename V>
+MMF_HD void ph_z_gather(V (&a)[9], V (&b)[8], const typename CxTraits<V>::Xe* xb, int tau) {
   using C = FftCfg<NFFT>;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int k = tau + C::TPF * r;
-    const float2 a = xb[k];
-    const float2 b = xb[(C::M - k) & (C::M - 1)];
-    const float2 p = split_pair(a, b, w32(r), wtau);
-    ptile[k * ppitch + t] = p.x;
-    ptile[(C::M - k) * ppitch + t] = p.y;
+    xset<PART>(a[r], xb[k]);
+    xset<PART>(b[r], xb[(C::M - k) & (C::M - 1)]);
+  }
+  xset<PART>(a[8], xb[C::M / 2]);
+}
+
+// ---- split step for one conjugate pair: a = Z[k], b = Z[(M-k) mod M] (both
+// already scaled by 1/2 through the window).  Returns |X[k]|^2 in .x and
+// |X[M-k]|^2 in .y (for two frames: each a pk of (frame A, frame B)).
+// wk = e^{-2*pi*i*k/NFFT} is applied as c32[r] (compile-time) then wtau.
+template <typename V>
+MMF_HD V split_pair(V a, V b, float2 c32r, typename CxTraits<V>::Tw wtau) {
+  const V E = cx<V>(sadd(a.x, b.x), ssub(a.y, b.y));
+  const V O = cx<V>(sadd(a.y, b.y), ssub(b.x, a.x));
+  const V WO = cmul(cmul(O, make_tw<V>(c32r)), wtau);
+  const V Xp = cadd(E, WO), Xm = csub(E, WO);
+  return cx<V>(sfma(Xp.x, Xp.x, smul(Xp.y, Xp.y)), sfma(Xm.x, Xm.x, smul(Xm.y, Xm.y)));
+}
+
+// power of bin k of frame t (float) / frames t, t+1 (pk; t even, ppitch even)
+MMF_HD void ptile_store(float* ptile, int idx, float p) { ptile[idx] = p; }
+MMF_HD void ptile_store(float* ptile, int idx, pk p) { *reinterpret_cast<pk*>(ptile + idx) = p; }
+
+// ---- split step from gathered pairs (any NFFT).
+// Thread tau handles k = tau + TPF*r, r = 0..7 (covers [0, M/2)); tau == 0 also k = M/2.
+// Power lands in ptile[k*ppitch + t].
+template <int NFFT, typename V>
+MMF_HD void ph_split_pairs(const V (&a)[9], const V (&b)[8], float* ptile, int ppitch, int t, int tau,
+                           typename CxTraits<V>::Tw wtau) {
+  using C = FftCfg<NFFT>;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int k = tau + C::TPF * r;
+    const V p = split_pair(a[r], b[r], w32(r), wtau);
+    ptile_store(ptile, k * ppitch + t, p.x);
+    ptile_store(ptile, (C::M - k) * ppitch + t, p.y);
   }
   if (tau == 0) {
-    const float2 a = xb[C::M / 2];
-    const float2 p = split_pair(a, a, w32(8), wtau);
-    ptile[(C::M / 2) * ppitch + t] = p.x;
+    const V p = split_pair(a[8], a[8], w32(8), wtau);
+    ptile_store(ptile, (C::M / 2) * ppitch + t, p.x);
   }
+}
+
+// one-frame convenience used by the host emulator and the trajectory-FFT kernel
+template <int NFFT>
+MMF_HD void ph_split_smem(const float2* xb, float* ptile, int ppitch, int t, int tau, float2 wtau) {
+  float2 a[9], b[8];
+  ph_z_gather<NFFT>(a, b, xb, tau);
+  ph_split_pairs<NFFT>(a, b, ptile, ppitch, t, tau, wtau);
 }
 
 // Same, handing each (bin, power) to a callback instead of a power tile
@@ -243,19 +340,20 @@ MMF_HD void ph_split_smem_cb(const float2* xb, int tau, float2 wtau, Emit emit) 
 // s = tau holds Z[16*j2 + s] in v[j2].  bpart[r] must hold Z[M - (16*r + s)]:
 // on the device it is v[15 - r] of lane (16 - s) & 15 (one shuffle per float);
 // for s == 0 it is the thread's own v[(16 - r) & 15].
-MMF_HD void ph_split_regs512(const float2 (&v)[16], const float2 (&bpart)[8], float* ptile, int ppitch, int t,
-                             int s, float2 wtau) {
+template <typename V>
+MMF_HD void ph_split_regs512(const V (&v)[16], const V (&bpart)[8], float* ptile, int ppitch, int t, int s,
+                             typename CxTraits<V>::Tw wtau) {
   constexpr int M = 256;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int k = 16 * r + s;
-    const float2 p = split_pair(v[r], bpart[r], w32(r), wtau);
-    ptile[k * ppitch + t] = p.x;
-    ptile[(M - k) * ppitch + t] = p.y;
+    const V p = split_pair(v[r], bpart[r], w32(r), wtau);
+    ptile_store(ptile, k * ppitch + t, p.x);
+    ptile_store(ptile, (M - k) * ppitch + t, p.y);
   }
   if (s == 0) {
-    const float2 p = split_pair(v[8], v[8], w32(8), wtau);
-    ptile[(M / 2) * ppitch + t] = p.x;
+    const V p = split_pair(v[8], v[8], w32(8), wtau);
+    ptile_store(ptile, (M / 2) * ppitch + t, p.x);
   }
 }
 

@@ -91,45 +91,113 @@ __device__ __forceinline__ void issue_span(const CUtensorMap* tmap, const StftAr
   for (int bx = 0; bx < p.span_alloc / kBox; ++bx) tma_load_2d(dst + bx * kBox, tmap, g0 + bx * kBox, clip, bar);
 }
 
-template <int NFFT>
+// shuffle of a complex value from lane src (one shuffle per 32-bit half)
+__device__ __forceinline__ float2 shfl_cx(float2 v, int src) {
+  return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ c2 shfl_cx(c2 v, int src) {
+  const float xa = __shfl_sync(0xffffffffu, plo(v.x), src), xb = __shfl_sync(0xffffffffu, phi(v.x), src);
+  const float ya = __shfl_sync(0xffffffffu, plo(v.y), src), yb = __shfl_sync(0xffffffffu, phi(v.y), src);
+  return CxTraits<c2>::make(pmake(xa, xb), pmake(ya, yb));
+}
+
+// ---- tensor-core mel projection -------------------------------------------------
+// D[frame][band] += A[frame][bin] * B[bin][band] with mma.sync m16n8k8 TF32, three MMAs per
+// product (hi*hi + hi*lo + lo*hi, fp32 accumulate): single-pass TF32 fails the 1e-4 tolerance
+// on mel power, the 3-term split is accurate to ~2^-21.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_log2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+constexpr int kMaxUnits = 16;  // (n-tile, m-tile) units per warp: n_mels <= 512 -> 64 n-tiles x 2 / 8 warps
+
+// V = float2: one frame per thread group; V = c2: two adjacent frames per thread group on
+// packed FP32 instructions (fft_regs.cuh)
+template <int NFFT, typename V>
 __global__ void __launch_bounds__(kThreads, 2)
     stft_mel_kernel(const __grid_constant__ CUtensorMap tmap, const StftArgs p) {
   using C = FftCfg<NFFT>;
-  constexpr int FPI = kThreads / C::TPF;  // frames transformed per iteration
+  using TR = CxTraits<V>;
+  using Tw = typename TR::Tw;
+  using Xe = typename TR::Xe;
+  constexpr int SLOTS = kThreads / C::TPF;      // thread groups (one or two frames each)
+  constexpr int FPI = SLOTS * TR::kFrames;      // frames transformed per iteration
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 
   // ---- shared memory carve-up (mirrors stft_smem_bytes() on the host)
   float* s_span = reinterpret_cast<float*>(smem_raw);                       // [span_bufs][span_alloc]
   float* s_ptile = s_span + p.span_bufs * p.span_alloc;                     // [pt_bufs][F*ppitch]
-  float2* s_xb = reinterpret_cast<float2*>(s_ptile + ((p.pt_bufs * C::F * p.ppitch + 3) & ~3));  // [FPI][XBUF]
-  float2* s_tw1 = s_xb + FPI * C::XBUF;                                     // [TW1]
-  float2* s_tw2 = s_tw1 + C::TW1;                                           // [TW2]
-  float2* s_w2 = s_tw2 + C::TW2;                                            // [F]
-  int* s_seg = reinterpret_cast<int*>(s_w2 + C::F);                         // [n_mels + 2]
-  int* s_mb = s_seg + ((p.n_mels + 2 + 1) & ~1);                            // [kMaxWorkers + 2] band-group bounds
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mb + kMaxWorkers + 2);    // [2]
+  constexpr int FP = (C::F + 7) & ~7;  // bin rows padded to the MMA K tile; the pad rows stay zero
+  Xe* s_xb = reinterpret_cast<Xe*>(s_ptile + ((p.pt_bufs * FP * p.ppitch + 3) & ~3));  // [SLOTS][XBUF]
+  Tw* s_tw1 = reinterpret_cast<Tw*>(s_xb + SLOTS * C::XBUF);                // [TW1]
+  Tw* s_tw2 = s_tw1 + C::TW1;                                               // [TW2]
+  float2* s_win = reinterpret_cast<float2*>(s_tw2 + C::TW2);                // [M] half-scaled window pairs
+  // mel tables: sparse FP32 walk            | tensor cores
+  //   s_w2  [F] (falling, rising) weights   |   s_bw    [n_pairs][32] B fragments (fp32, split on the fly)
+  //   s_seg [n_mels + 2] segment starts     |   s_pk8   [n_pairs] k-tile of each pair
+  //   s_mb  [kMaxWorkers + 2] band groups   |   s_npair [NT + 1] pair range of each 8-band n-tile
+  //                                         |   s_units [8][kMaxUnits] (n | m << 8) work list per warp
+  float2* s_w2 = s_win + C::M;
+  int* s_seg = reinterpret_cast<int*>(s_w2 + C::F);
+  int* s_mb = s_seg + ((p.n_mels + 2 + 1) & ~1);
+  float2* s_bw = s_win + C::M;
+  int* s_pk8 = reinterpret_cast<int*>(s_bw + (size_t)p.mma_n_pairs * 32);
+  int* s_npair = s_pk8 + p.mma_n_pairs;
+  int* s_units = s_npair + ((p.n_mels + 7) / 8 + 1);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(
+      reinterpret_cast<unsigned char*>(s_win + C::M) + ((p.mel_tab_bytes + 15) & ~15));  // [2]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int tau = tid % C::TPF;
   const int slot = tid / C::TPF;
 
-  for (int i = tid; i < C::TW1; i += kThreads) s_tw1[i] = p.tw1[i];
-  for (int i = tid; i < C::TW2; i += kThreads) s_tw2[i] = p.tw2[i];
-  for (int i = tid; i < C::F; i += kThreads) s_w2[i] = p.w2[i];
-  for (int i = tid; i < p.n_mels + 2; i += kThreads) s_seg[i] = p.seg_start[i];
-  for (int i = tid; i < kMaxWorkers + 1; i += kThreads) s_mb[i] = p.band_split[i];
-
-  // Hann window of this thread's 16 complex points, pre-scaled by the 1/2 of the split step
-  float2 wreg[16];
-#pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) {
-    const int c = tau + C::TPF * n2;
-    const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * c);
-    wreg[n2] = make_float2(0.5f * w.x, 0.5f * w.y);
+  for (int i = tid; i < C::TW1; i += kThreads) s_tw1[i] = make_tw<V>(p.tw1[i]);
+  for (int i = tid; i < C::TW2; i += kThreads) s_tw2[i] = make_tw<V>(p.tw2[i]);
+  if (p.mel_mma) {
+    const int NT = (p.n_mels + 7) / 8;
+    for (int i = tid; i < p.mma_n_pairs * 32; i += kThreads) s_bw[i] = p.mma_bw[i];
+    for (int i = tid; i < p.mma_n_pairs; i += kThreads) s_pk8[i] = p.mma_pk8[i];
+    for (int i = tid; i < NT + 1; i += kThreads) s_npair[i] = p.mma_npair[i];
+    for (int i = tid; i < 8 * kMaxUnits; i += kThreads) s_units[i] = p.mma_units[i];
+  } else {
+    for (int i = tid; i < C::F; i += kThreads) s_w2[i] = p.w2[i];
+    for (int i = tid; i < p.n_mels + 2; i += kThreads) s_seg[i] = p.seg_start[i];
+    for (int i = tid; i < kMaxWorkers + 1; i += kThreads) s_mb[i] = p.band_split[i];
   }
-  float2 wtau;
-  sincospif(-2.0f * (float)tau / (float)NFFT, &wtau.y, &wtau.x);
+  for (int i = tid; i < p.pt_bufs * FP * p.ppitch; i += kThreads) s_ptile[i] = 0.0f;  // incl. the K pad rows
+
+  // Hann window pre-scaled by the 1/2 of the split step.  One frame per thread group: the
+  // thread's 16 complex points stay in registers; two frames: registers are needed for the
+  // second frame, so the window is staged in shared memory and re-read per iteration.
+  constexpr bool kWinRegs = TR::kFrames == 1;
+  for (int i = tid; i < C::M; i += kThreads) {
+    const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * i);
+    s_win[i] = make_float2(0.5f * w.x, 0.5f * w.y);
+  }
+  float2 wreg[16];
+  if constexpr (kWinRegs) {
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const int c = tau + C::TPF * n2;
+      const float2 w = *reinterpret_cast<const float2*>(p.window + 2 * c);
+      wreg[n2] = make_float2(0.5f * w.x, 0.5f * w.y);
+    }
+  }
+  Tw wtau;
+  {
+    float2 w;
+    sincospif(-2.0f * (float)tau / (float)NFFT, &w.y, &w.x);
+    wtau = make_tw<V>(w);
+  }
 
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
@@ -152,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     // the span starts at the 16-byte aligned sample at or below the first needed one
     const int g_first = t0 * p.hop - NFFT / 2 - lead;
     const int shift = g_first - (g_first & ~3);
-    float* ptile = s_ptile + (size_t)(p.pt_bufs == 2 ? (it & 1) : 0) * C::F * p.ppitch;
+    float* ptile = s_ptile + (size_t)(p.pt_bufs == 2 ? (it & 1) : 0) * FP * p.ppitch;
 
     if (p.use_tma) {
       // two span buffers: prefetch the next tile into the other one now (its last readers
@@ -173,31 +241,64 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
 
     // ---------------- FFT phase: FPI frames per iteration ----------------
-    float2* xb = s_xb + slot * C::XBUF;
-    for (int fi = 0; fi < p.TF / FPI; ++fi) {
-      const int f = fi * FPI + slot;
+    Xe* xb = s_xb + slot * C::XBUF;
+    auto fsync = [] { frame_sync<C::TPF>(); };
+    for (int fi = 0; fi < ((p.debug_skip & 1) ? 0 : p.TF / FPI); ++fi) {
+      const int f = (fi * SLOTS + slot) * TR::kFrames;  // first (or only) frame of this thread group
       const int off = shift + lead + f * p.hop;
-      float2 v[16];
+      V v[16];
+      if constexpr (!kWinRegs) {
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) wreg[n2] = s_win[tau + C::TPF * n2];
+      }
       if (p.preemph != 0.0f) {
         // samples from this frame's start to the end of the clip (frame start = f*hop - n_fft/2)
         const long n_valid = p.n_samples - ((long)(t0 + f) * p.hop - NFFT / 2);
-        ph_load_pre<NFFT>(v, span, off, tau, wreg, p.preemph, n_valid);
+        ph_load_pre<NFFT>(v, span, off, p.hop, tau, wreg, p.preemph, n_valid);
       } else if (p.vec_ok && !(shift & 1)) {
-        ph_load<NFFT, true>(v, span, off, tau, wreg);
+        ph_load<NFFT, true>(v, span, off, p.hop, tau, wreg);
       } else {
-        ph_load<NFFT, false>(v, span, off, tau, wreg);
+        ph_load<NFFT, false>(v, span, off, p.hop, tau, wreg);
+      }
+      if (p.use_tma && p.span_bufs == 1 && p.early_tma && fi == p.TF / FPI - 1) {
+        // every frame of the tile now sits in registers: the single span buffer is free, so the
+        // next tile's PCM streams in underneath this tile's transform and mel projection
+        __syncthreads();
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span, &s_bar[0]);
       }
       ph_pass1<NFFT>(v, s_tw1, tau);
-      frame_sync<C::TPF>();  // previous iteration's readers of xb are done
-      ph_x1_write<NFFT>(v, xb, tau);
-      frame_sync<C::TPF>();
-      ph_x1_read<NFFT>(v, xb, tau);
+      if constexpr (TR::kXParts == 1) {
+        fsync();  // previous iteration's readers of xb are done
+        ph_x1_write<NFFT, 0>(v, xb, tau);
+        fsync();
+        ph_x1_read<NFFT, 0>(v, xb, tau);
+      } else {
+        fsync();
+        ph_x1_write<NFFT, 1>(v, xb, tau);
+        fsync();
+        ph_x1_read<NFFT, 1>(v, xb, tau);
+        fsync();
+        ph_x1_write<NFFT, 2>(v, xb, tau);
+        fsync();
+        ph_x1_read<NFFT, 2>(v, xb, tau);
+      }
       ph_pass2<NFFT>(v, s_tw2, tau);
       if constexpr (C::R3 > 1) {
-        frame_sync<C::TPF>();
-        ph_x2_write<NFFT>(v, xb, tau);
-        frame_sync<C::TPF>();
-        ph_x2_read<NFFT>(v, xb, tau);
+        if constexpr (TR::kXParts == 1) {
+          fsync();
+          ph_x2_write<NFFT, 0>(v, xb, tau);
+          fsync();
+          ph_x2_read<NFFT, 0>(v, xb, tau);
+        } else {
+          fsync();
+          ph_x2_write<NFFT, 1>(v, xb, tau);
+          fsync();
+          ph_x2_read<NFFT, 1>(v, xb, tau);
+          fsync();
+          ph_x2_write<NFFT, 2>(v, xb, tau);
+          fsync();
+          ph_x2_read<NFFT, 2>(v, xb, tau);
+        }
         ph_pass3<NFFT>(v);
       }
       bool done = false;
@@ -205,28 +306,39 @@ __global__ void __launch_bounds__(kThreads, 2)
         if (p.split_regs) {
           // partner lane holds Z[M-k]: lane (16 - s) & 15 of the same half-warp, register 15 - r
           const int src = ((16 - tau) & 15) | (lane & 16);
-          float2 bpart[8];
+          V bpart[8];
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            const float bx = __shfl_sync(0xffffffffu, v[15 - r].x, src);
-            const float by = __shfl_sync(0xffffffffu, v[15 - r].y, src);
-            const float2 own = v[(16 - r) & 15];
-            bpart[r] = (tau == 0) ? own : make_float2(bx, by);
+            const V sh = shfl_cx(v[15 - r], src);
+            bpart[r] = (tau == 0) ? v[(16 - r) & 15] : sh;
           }
           ph_split_regs512(v, bpart, ptile, p.ppitch, f, tau, wtau);
           done = true;
         }
       }
       if (!done) {
-        frame_sync<C::TPF>();
-        ph_z_write<NFFT>(v, xb, tau);
-        frame_sync<C::TPF>();
-        ph_split_smem<NFFT>(xb, ptile, p.ppitch, f, tau, wtau);
+        V za[9], zb[8];
+        if constexpr (TR::kXParts == 1) {
+          fsync();
+          ph_z_write<NFFT, 0>(v, xb, tau);
+          fsync();
+          ph_z_gather<NFFT, 0>(za, zb, xb, tau);
+        } else {
+          fsync();
+          ph_z_write<NFFT, 1>(v, xb, tau);
+          fsync();
+          ph_z_gather<NFFT, 1>(za, zb, xb, tau);
+          fsync();
+          ph_z_write<NFFT, 2>(v, xb, tau);
+          fsync();
+          ph_z_gather<NFFT, 2>(za, zb, xb, tau);
+        }
+        ph_split_pairs<NFFT>(za, zb, ptile, p.ppitch, f, tau, wtau);
       }
     }
-    __syncthreads();  // power tile complete; span[b] no longer needed
-    if (p.use_tma && p.span_bufs == 1 && tid == 0 && tile + gridDim.x < n_tiles)
-      issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span, &s_bar[0]);  // streams in during the mel phase
+    __syncthreads();  // power tile complete
+    if (p.use_tma && p.span_bufs == 1 && (!p.early_tma || (p.debug_skip & 1)) && tid == 0 && tile + gridDim.x < n_tiles)
+      issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span, &s_bar[0]);  // (profiling mode without FFT phase)
 
     const int t_valid = min(p.TF, p.T - t0);
     if (p.power != nullptr) {
@@ -236,7 +348,62 @@ __global__ void __launch_bounds__(kThreads, 2)
         if (t < t_valid) dst[(size_t)k * p.T + t] = ptile[k * p.ppitch + t];
       }
     }
-    if (p.logmel != nullptr) {
+    if (p.logmel != nullptr && p.mel_mma && !(p.debug_skip & 2)) {
+      // ---------------- mel phase on the tensor cores.
+      // D[frame][band] = P[frame][bin] * W[bin][band] in 16x8 output tiles.  Only the (n-tile,
+      // k-tile) blocks of the filterbank that are not all zero are listed (n-major, built on the
+      // host).  A unit = one 8-band n-tile x one 16-frame m-tile, owned by exactly one warp
+      // (longest-processing-time assignment on the host), so the accumulators go from
+      // registers through log10 straight to global memory: no atomics, no staging tile.
+      const int warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+      float mx = -FLT_MAX;
+      for (int ui = 0; ui < kMaxUnits; ++ui) {
+        const int unit = s_units[warp * kMaxUnits + ui];
+        if (unit < 0) break;
+        const int n = unit & 0xff, m = unit >> 8;
+        // one accumulator per split term: three independent MMA chains instead of one
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc_hl[4] = {0.0f, 0.0f, 0.0f, 0.0f},
+              acc_lh[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const int q0 = s_npair[n], q1 = s_npair[n + 1];
+        const float* pbase = ptile + t4 * p.ppitch + 16 * m + g;
+        const int p4 = 4 * p.ppitch;
+#pragma unroll 2
+        for (int q = q0; q < q1; ++q) {
+          const float2 bw = s_bw[q * 32 + lane];
+          const float* pa = pbase + s_pk8[q] * 8 * p.ppitch;
+          const float a[4] = {pa[0], pa[8], pa[p4], pa[p4 + 8]};
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ah[e] = __float_as_uint(a[e]) & 0xffffe000u;  // TF32 keeps 10 mantissa bits
+            al[e] = __float_as_uint(a[e] - __uint_as_float(ah[e]));
+          }
+          const uint32_t bh0 = __float_as_uint(bw.x) & 0xffffe000u, bh1 = __float_as_uint(bw.y) & 0xffffe000u;
+          const uint32_t bl0 = __float_as_uint(bw.x - __uint_as_float(bh0));
+          const uint32_t bl1 = __float_as_uint(bw.y - __uint_as_float(bh1));
+          mma_tf32(acc, ah, bh0, bh1);
+          mma_tf32(acc_hl, ah, bl0, bl1);
+          mma_tf32(acc_lh, al, bh0, bh1);
+        }
+        // acc: (frame g, band 2*t4), (g, 2*t4+1), (g+8, 2*t4), (g+8, 2*t4+1) of this unit
+        const int band0 = 8 * n + 2 * t4;
+        float* orow = p.logmel + ((size_t)clip * p.n_mels + band0) * p.T + t0 + 16 * m + g;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int f = 16 * m + g + ((e & 2) ? 8 : 0);
+          if (f < t_valid && band0 + (e & 1) < p.n_mels) {
+            // 10*log10(x) = 10*log10(2) * log2(x); lg2.approx is within 1e-6 dB here (x >= amin, never denormal)
+            const float val = acc[e] + (acc_hl[e] + acc_lh[e]);
+            const float db = 3.01029995663981195f * fast_log2(fmaxf(p.amin, val));
+            orow[((e & 1) ? p.T : 0) + ((e & 2) ? 8 : 0)] = db;
+            mx = fmaxf(mx, db);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0 && mx > -FLT_MAX) atomicMax(p.clipmax + clip, float_key(mx));
+    } else if (p.logmel != nullptr && !(p.debug_skip & 2)) {
       // ---------------- mel phase: lane -> frame, worker (warp or part of one) -> band group.
       // Band groups are balanced on the host by bins + bands (c_api.cu: band_split).
       const int t = lane % p.TF;
@@ -249,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         const int T = p.T;
         auto emit = [&](int, float val) {
           // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is within 1e-6 dB here (x >= amin, never denormal)
-          const float db = 3.01029995663981195f * __log2f(fmaxf(amin, val));
+          const float db = 3.01029995663981195f * fast_log2(fmaxf(amin, val));
           *dst = db;
           dst += T;
           mx = fmaxf(mx, db);
@@ -274,66 +441,88 @@ __global__ void __launch_bounds__(kThreads, 2)
 // host side
 // ---------------------------------------------------------------------------
 
+size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs) {
+  const int F = n_fft / 2 + 1;
+  if (mel_mma)
+    return (size_t)n_pairs * 32 * 8 + (size_t)n_pairs * 4 + (size_t)((n_mels + 7) / 8 + 1) * 4 + 8 * kMaxUnits * 4;
+  return (size_t)F * 8 + (size_t)((n_mels + 2 + 1) & ~1) * 4 + (size_t)(kMaxWorkers + 2) * 4;
+}
+
 template <int NFFT>
-static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_bufs, int n_mels) {
+static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed, size_t mel_tab_bytes) {
   using C = FftCfg<NFFT>;
-  constexpr int FPI = kThreads / C::TPF;
+  constexpr int SLOTS = kThreads / C::TPF;
+  constexpr int FP = (C::F + 7) & ~7;
+  const size_t tw_bytes = packed ? sizeof(c2) : sizeof(float2);
   size_t b = 0;
   b += (size_t)span_bufs * span_alloc * 4;
-  b += (size_t)((pt_bufs * C::F * ppitch + 3) & ~3) * 4;
-  b += (size_t)FPI * C::XBUF * 8;
-  b += (size_t)(C::TW1 + C::TW2 + C::F) * 8;
-  b += (size_t)((n_mels + 2 + 1) & ~1) * 4;
-  b += (size_t)(kMaxWorkers + 2) * 4;
+  b += (size_t)((pt_bufs * FP * ppitch + 3) & ~3) * 4;
+  b += (size_t)SLOTS * C::XBUF * 8;
+  b += (size_t)(C::TW1 + C::TW2) * tw_bytes;
+  b += (size_t)C::M * 8;
+  b += (mel_tab_bytes + 15) & ~(size_t)15;
   b += 16;
   return b;
 }
 
 template <int NFFT>
-static void geometry_t(StftGeometry* g) {
+static void geometry_t(StftGeometry* g, int packed) {
   using C = FftCfg<NFFT>;
   g->tpf = C::TPF;
-  g->fpi = kThreads / C::TPF;
+  g->fpi = (kThreads / C::TPF) * (packed ? 2 : 1);
   g->tw1 = C::TW1;
   g->tw2 = C::TW2;
   g->r3 = C::R3;
   g->m = C::M;
 }
 
-int stft_geometry(int n_fft, StftGeometry* g) {
+// two frames per thread group need <= 32 frames per iteration (one frame per lane in the mel phase)
+bool stft_packed_supported(int n_fft) { return n_fft >= 512; }
+
+int stft_geometry(int n_fft, int packed, StftGeometry* g) {
   switch (n_fft) {
-    case 256: geometry_t<256>(g); return 0;
-    case 512: geometry_t<512>(g); return 0;
-    case 1024: geometry_t<1024>(g); return 0;
-    case 2048: geometry_t<2048>(g); return 0;
-    case 4096: geometry_t<4096>(g); return 0;
+    case 256: geometry_t<256>(g, packed); return 0;
+    case 512: geometry_t<512>(g, packed); return 0;
+    case 1024: geometry_t<1024>(g, packed); return 0;
+    case 2048: geometry_t<2048>(g, packed); return 0;
+    case 4096: geometry_t<4096>(g, packed); return 0;
     default: return -1;
   }
 }
 
-size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int n_mels) {
+size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed,
+                       size_t mel_tab_bytes) {
   switch (n_fft) {
-    case 256: return smem_bytes_t<256>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
-    case 512: return smem_bytes_t<512>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
-    case 1024: return smem_bytes_t<1024>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
-    case 2048: return smem_bytes_t<2048>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
-    case 4096: return smem_bytes_t<4096>(span_alloc, span_bufs, ppitch, pt_bufs, n_mels);
+    case 256: return smem_bytes_t<256>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
+    case 512: return smem_bytes_t<512>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
+    case 1024: return smem_bytes_t<1024>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
+    case 2048: return smem_bytes_t<2048>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
+    case 4096: return smem_bytes_t<4096>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
     default: return 0;
   }
 }
 
-template <int NFFT>
-static cudaError_t launch_t(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
+template <int NFFT, typename V>
+static cudaError_t launch_v(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(stft_mel_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e =
+        cudaFuncSetAttribute(stft_mel_kernel<NFFT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  stft_mel_kernel<NFFT><<<grid, kThreads, smem, st>>>(tmap, a);
+  stft_mel_kernel<NFFT, V><<<grid, kThreads, smem, st>>>(tmap, a);
   return cudaGetLastError();
+}
+
+template <int NFFT>
+static cudaError_t launch_t(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
+  if constexpr (NFFT >= 512) {
+    if (a.packed) return launch_v<NFFT, c2>(tmap, a, grid, smem, st);
+  }
+  return launch_v<NFFT, float2>(tmap, a, grid, smem, st);
 }
 
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,

@@ -14,29 +14,44 @@
 
 using namespace mmf;
 
-template <int NFFT>
+// V = float2: one frame at a time; V = c2: frames (t, t+1) together through the packed-type path
+template <int NFFT, typename V>
 static void run(const float* y, long n, int hop, const float* window, float* power, long T, int regs_split) {
   using C = FftCfg<NFFT>;
+  using TR = CxTraits<V>;
+  using Tw = typename TR::Tw;
+  using Xe = typename TR::Xe;
+  constexpr int NF = TR::kFrames;
   const int pad = NFFT / 2;
-  std::vector<float> ypad(n + 2 * pad + NFFT, 0.0f);
+  std::vector<float> ypad(n + 2 * pad + NFFT + (size_t)hop * NF, 0.0f);
   std::memcpy(ypad.data() + pad, y, sizeof(float) * n);
   // tables exactly as the plan builds them
-  std::vector<float2> tw1(C::TW1), tw2(C::TW2 > 0 ? C::TW2 : 1);
+  std::vector<Tw> tw1(C::TW1), tw2(C::TW2 > 0 ? C::TW2 : 1);
   for (int k2 = 0; k2 < 16; ++k2)
     for (int n1 = 0; n1 < C::TPF; ++n1) {
       double a = -2.0 * M_PI * (double)((long)n1 * k2 % C::M) / C::M;
-      tw1[k2 * C::TPF + n1] = make_float2((float)cos(a), (float)sin(a));
+      tw1[k2 * C::TPF + n1] = make_tw<V>(make_float2((float)cos(a), (float)sin(a)));
     }
   for (int j2 = 0; j2 < 16; ++j2)
     for (int m1 = 0; m1 < C::R3; ++m1) {
       double a = -2.0 * M_PI * (double)(m1 * j2 % C::TPF) / C::TPF;
-      tw2[j2 * C::R3 + m1] = make_float2((float)cos(a), (float)sin(a));
+      tw2[j2 * C::R3 + m1] = make_tw<V>(make_float2((float)cos(a), (float)sin(a)));
     }
-  std::vector<float2> xb(C::XBUF);
-  std::vector<float> ptile(C::F);
-  std::vector<float2> regs(C::TPF * 16);
-  auto R = [&](int tau) -> float2(&)[16] { return *reinterpret_cast<float2(*)[16]>(&regs[tau * 16]); };
-  for (long t = 0; t < T; ++t) {
+  std::vector<Xe> xb(C::XBUF);
+  const int pp = 2;  // power-tile pitch: two frames side by side
+  std::vector<float> ptile((size_t)C::F * pp);
+  std::vector<V> regs(C::TPF * 16);
+  auto R = [&](int tau) -> V(&)[16] { return *reinterpret_cast<V(*)[16]>(&regs[tau * 16]); };
+  auto wt = [&](int tau) {
+    double a = -2.0 * M_PI * tau / NFFT;
+    return make_tw<V>(make_float2((float)cos(a), (float)sin(a)));
+  };
+  // one exchange = write by all threads, then read by all threads; the two-frame path runs it per component
+  auto xchg = [&](auto wr, auto rd) {
+    for (int tau = 0; tau < C::TPF; ++tau) wr(tau);
+    for (int tau = 0; tau < C::TPF; ++tau) rd(tau);
+  };
+  for (long t = 0; t < T; t += NF) {
     const float* span = ypad.data();
     const int off = (int)(t * hop);
     for (int tau = 0; tau < C::TPF; ++tau) {
@@ -45,51 +60,82 @@ static void run(const float* y, long n, int hop, const float* window, float* pow
         int c = tau + C::TPF * n2;
         wreg[n2] = make_float2(0.5f * window[2 * c], 0.5f * window[2 * c + 1]);
       }
-      ph_load<NFFT, false>(R(tau), span, off, tau, wreg);
+      ph_load<NFFT, false>(R(tau), span, off, hop, tau, wreg);
       ph_pass1<NFFT>(R(tau), tw1.data(), tau);
-      ph_x1_write<NFFT>(R(tau), xb.data(), tau);
     }
-    for (int tau = 0; tau < C::TPF; ++tau) ph_x1_read<NFFT>(R(tau), xb.data(), tau);
+    if constexpr (NF == 1) {
+      xchg([&](int tau) { ph_x1_write<NFFT, 0>(R(tau), xb.data(), tau); },
+           [&](int tau) { ph_x1_read<NFFT, 0>(R(tau), xb.data(), tau); });
+    } else {
+      xchg([&](int tau) { ph_x1_write<NFFT, 1>(R(tau), xb.data(), tau); },
+           [&](int tau) { ph_x1_read<NFFT, 1>(R(tau), xb.data(), tau); });
+      xchg([&](int tau) { ph_x1_write<NFFT, 2>(R(tau), xb.data(), tau); },
+           [&](int tau) { ph_x1_read<NFFT, 2>(R(tau), xb.data(), tau); });
+    }
     for (int tau = 0; tau < C::TPF; ++tau) ph_pass2<NFFT>(R(tau), tw2.data(), tau);
     if (C::R3 > 1) {
-      for (int tau = 0; tau < C::TPF; ++tau) ph_x2_write<NFFT>(R(tau), xb.data(), tau);
-      for (int tau = 0; tau < C::TPF; ++tau) ph_x2_read<NFFT>(R(tau), xb.data(), tau);
+      if constexpr (NF == 1) {
+        xchg([&](int tau) { ph_x2_write<NFFT, 0>(R(tau), xb.data(), tau); },
+             [&](int tau) { ph_x2_read<NFFT, 0>(R(tau), xb.data(), tau); });
+      } else {
+        xchg([&](int tau) { ph_x2_write<NFFT, 1>(R(tau), xb.data(), tau); },
+             [&](int tau) { ph_x2_read<NFFT, 1>(R(tau), xb.data(), tau); });
+        xchg([&](int tau) { ph_x2_write<NFFT, 2>(R(tau), xb.data(), tau); },
+             [&](int tau) { ph_x2_read<NFFT, 2>(R(tau), xb.data(), tau); });
+      }
       for (int tau = 0; tau < C::TPF; ++tau) ph_pass3<NFFT>(R(tau));
     }
     if (NFFT == 512 && regs_split) {
       for (int s = 0; s < 16; ++s) {
-        float2 bpart[8];
+        V bpart[8];
         const int partner = (16 - s) & 15;
         for (int r = 0; r < 8; ++r) {
-          float2 sh = R(partner)[15 - r];        // what shuffle #r delivers
-          float2 own = R(s)[(16 - r) & 15];      // lane-0 special case
+          V sh = R(partner)[15 - r];        // what the shuffles of round r deliver
+          V own = R(s)[(16 - r) & 15];      // lane-0 special case
           bpart[r] = (s == 0) ? own : sh;
         }
-        double a = -2.0 * M_PI * s / NFFT;
-        ph_split_regs512(R(s), bpart, ptile.data(), 1, 0, s, make_float2((float)cos(a), (float)sin(a)));
+        ph_split_regs512(R(s), bpart, ptile.data(), pp, 0, s, wt(s));
       }
     } else {
-      for (int tau = 0; tau < C::TPF; ++tau) ph_z_write<NFFT>(R(tau), xb.data(), tau);
-      for (int tau = 0; tau < C::TPF; ++tau) {
-        double a = -2.0 * M_PI * tau / NFFT;
-        ph_split_smem<NFFT>(xb.data(), ptile.data(), 1, 0, tau, make_float2((float)cos(a), (float)sin(a)));
+      std::vector<V> za((size_t)C::TPF * 9), zb((size_t)C::TPF * 8);
+      auto ZA = [&](int tau) -> V(&)[9] { return *reinterpret_cast<V(*)[9]>(&za[(size_t)tau * 9]); };
+      auto ZB = [&](int tau) -> V(&)[8] { return *reinterpret_cast<V(*)[8]>(&zb[(size_t)tau * 8]); };
+      if constexpr (NF == 1) {
+        xchg([&](int tau) { ph_z_write<NFFT, 0>(R(tau), xb.data(), tau); },
+             [&](int tau) { ph_z_gather<NFFT, 0>(ZA(tau), ZB(tau), xb.data(), tau); });
+      } else {
+        xchg([&](int tau) { ph_z_write<NFFT, 1>(R(tau), xb.data(), tau); },
+             [&](int tau) { ph_z_gather<NFFT, 1>(ZA(tau), ZB(tau), xb.data(), tau); });
+        xchg([&](int tau) { ph_z_write<NFFT, 2>(R(tau), xb.data(), tau); },
+             [&](int tau) { ph_z_gather<NFFT, 2>(ZA(tau), ZB(tau), xb.data(), tau); });
       }
+      for (int tau = 0; tau < C::TPF; ++tau) ph_split_pairs<NFFT>(ZA(tau), ZB(tau), ptile.data(), pp, 0, tau, wt(tau));
     }
-    for (int k = 0; k < C::F; ++k) power[(long)k * T + t] = ptile[k];
+    for (int q = 0; q < NF && t + q < T; ++q)
+      for (int k = 0; k < C::F; ++k) power[(long)k * T + t + q] = ptile[(size_t)k * pp + q];
   }
 }
 
+template <int NFFT>
+static void run_any(const float* y, long n, int hop, const float* window, float* power, long T, int mode) {
+  // mode bit 0: register split (n_fft 512); bit 1: two-frame packed-type path
+  if (mode & 2)
+    run<NFFT, c2>(y, n, hop, window, power, T, mode & 1);
+  else
+    run<NFFT, float2>(y, n, hop, window, power, T, mode & 1);
+}
+
 extern "C" int emu_stft_power(const float* y, long n, int nfft, int hop, const float* window, float* power, long T,
-                              int regs_split) {
+                              int mode) {
   switch (nfft) {
-    case 32: run<32>(y, n, hop, window, power, T, regs_split); break;
-    case 64: run<64>(y, n, hop, window, power, T, regs_split); break;
-    case 128: run<128>(y, n, hop, window, power, T, regs_split); break;
-    case 256: run<256>(y, n, hop, window, power, T, regs_split); break;
-    case 512: run<512>(y, n, hop, window, power, T, regs_split); break;
-    case 1024: run<1024>(y, n, hop, window, power, T, regs_split); break;
-    case 2048: run<2048>(y, n, hop, window, power, T, regs_split); break;
-    case 4096: run<4096>(y, n, hop, window, power, T, regs_split); break;
+    case 32: run_any<32>(y, n, hop, window, power, T, mode); break;
+    case 64: run_any<64>(y, n, hop, window, power, T, mode); break;
+    case 128: run_any<128>(y, n, hop, window, power, T, mode); break;
+    case 256: run_any<256>(y, n, hop, window, power, T, mode); break;
+    case 512: run_any<512>(y, n, hop, window, power, T, mode); break;
+    case 1024: run_any<1024>(y, n, hop, window, power, T, mode); break;
+    case 2048: run_any<2048>(y, n, hop, window, power, T, mode); break;
+    case 4096: run_any<4096>(y, n, hop, window, power, T, mode); break;
     default: return -1;
   }
   return 0;

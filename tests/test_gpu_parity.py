@@ -173,6 +173,23 @@ def test_sosfiltfilt_bandpass_and_too_short(cuda_device):
     assert "greater than padlen, which is 21" in ei.value.msg
 
 
+@pytest.mark.parametrize("name", ["cfg1_16k", "gui_default", "cfg3_44k", "n1024"])
+@pytest.mark.parametrize("flags", [_lib.MMF_FLAG_SCALAR_FFT, _lib.MMF_FLAG_MMA_MEL,
+                                   _lib.MMF_FLAG_SCALAR_FFT | _lib.MMF_FLAG_MMA_MEL])
+def test_logmel_kernel_variants(name, flags, cuda_device):
+    """The non-default code paths of the fused kernel: one frame per thread group on
+    scalar FP32 (default: two frames on packed FFMA2/FADD2) and the mel projection on
+    the tensor cores (mma.sync TF32 x3; default: sparse FP32 walk)."""
+    cfg, secs = _cfg(name, flags=flags)
+    y = synth_batch(70, 3, int(cfg.sample_rate * secs), cfg.sample_rate)
+    plan = mm.get_plan(cfg)
+    lm, cmax = plan.logmel(y)
+    lm = lm.cpu().numpy()
+    for i in range(3):
+        _, _, unclamped = _oracle_unclamped(y[i], cfg)
+        assert _mel_rel_err(lm[i], unclamped) <= LOGMEL_REL, (name, flags)
+
+
 @pytest.mark.parametrize("T", [22, 45, 333, 1001, 2001, 2038, 2039, 5000])
 @pytest.mark.parametrize("order", [2, 6, 8, 10])
 def test_sosfiltfilt_chunk_parallel_and_sequential_paths(T, order, cuda_device):

@@ -260,10 +260,12 @@ def test_emulated_stft_matches_numpy(emu, nfft, sr, win, hop):
     w = oracle.padded_hann(win, nfft).astype(np.float32)
     T = oracle.n_frames(len(y), nfft, hop)
     ref = oracle.stft_power(y, nfft, hop, win)
-    for regs in ([0, 1] if nfft == 512 else [0]):
+    # mode bit 0: split step from registers (n_fft 512 only); bit 1: two frames per thread group
+    # through the packed value type (the code path of the FFMA2/FADD2 kernel)
+    for mode in ([0, 1, 2, 3] if nfft == 512 else [0, 2]):
         pw = np.zeros((nfft // 2 + 1, T), np.float32)
-        assert emu.emu_stft_power(_p(y), len(y), nfft, hop, _p(w), _p(pw), T, regs) == 0
-        assert np.max(np.abs(pw - ref)) / ref.max() < 1e-6
+        assert emu.emu_stft_power(_p(y), len(y), nfft, hop, _p(w), _p(pw), T, mode) == 0
+        assert np.max(np.abs(pw - ref)) / ref.max() < 1e-6, mode
 
 
 def _sparse_mel(cfg):
