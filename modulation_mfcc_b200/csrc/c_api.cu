@@ -582,13 +582,18 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   return MMF_OK;
 }
 
-// zero-phase IIR over independent rows: chunk-parallel kernel when the extended row
-// fits in shared memory (<= 2080 samples, <= 4 sections), else the sequential one
+// zero-phase IIR over independent rows: chunk-parallel kernel when the extended row fits in
+// shared memory (<= 6112 samples, <= 4 sections); super-block scan for long rows; else the
+// sequential kernel (many long rows, or more than 4 sections)
 static cudaError_t sosfiltfilt_any(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
                                    long group_stride, const SosArgs& a, double* y, long ys, cudaStream_t st) {
   SosPar par;
   if (sos_par_fill(a, T, &par))
     return sosfiltfilt_par_launch(x, x_is_f32, rows, T, xs, group_rows, group_stride, par, y, ys, st);
+  // long rows, few of them: the sequential kernel would walk every sample one by one
+  if (sos_long_supported(a, rows, T) && (size_t)rows * (size_t)(T + 2 * a.padlen) * 8 <= ((size_t)1 << 30) &&
+      !std::getenv("MMF_SOS_SEQUENTIAL"))
+    return sosfiltfilt_long_launch(x, x_is_f32, rows, T, xs, group_rows, group_stride, a, y, ys, st);
   return sosfiltfilt_launch_grouped(x, x_is_f32, rows, T, xs, group_rows, group_stride, a, y, ys, st);
 }
 

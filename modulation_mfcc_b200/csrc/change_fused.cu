@@ -28,15 +28,11 @@ static void host_sos_step(const SosPar& a, double v, double* z) {
   }
 }
 
-bool sos_par_fill(const SosArgs& src, long T, SosPar* out) {
+static bool sos_par_fill_cl(const SosArgs& src, int cl, SosPar* out) {
   if (src.n_sections < 1 || src.n_sections > kParMaxSections) return false;
-  const long L = T + 2L * src.padlen;
-  if (L > 32L * kSosParMaxChunk) return false;
   std::memset(out, 0, sizeof(*out));
   out->ns = src.n_sections;
   out->padlen = src.padlen;
-  int cl = (int)((L + 31) / 32);
-  if ((cl & 1) == 0) ++cl;
   out->CL = cl;
   for (int s = 0; s < src.n_sections; ++s) {
     for (int k = 0; k < 6; ++k) out->sos[s][k] = src.sos[s][k];
@@ -44,16 +40,26 @@ bool sos_par_fill(const SosArgs& src, long T, SosPar* out) {
     out->zi[s][1] = src.zi[s][1];
   }
   const int D = 2 * src.n_sections;
-  for (int jj = 0; jj < 5; ++jj) {
-    const long steps = (long)cl << jj;
+  // zero-input transition over `steps` samples, column by column
+  auto transition = [&](long steps, double (*m)[2 * kParMaxSections]) {
     for (int c = 0; c < D; ++c) {
       double z[2 * kParMaxSections] = {0};
       z[c] = 1.0;
       for (long i = 0; i < steps; ++i) host_sos_step(*out, 0.0, z);
-      for (int r = 0; r < D; ++r) out->mpow[jj][r][c] = z[r];
+      for (int r = 0; r < D; ++r) m[r][c] = z[r];
     }
-  }
+  };
+  for (int jj = 0; jj < 5; ++jj) transition((long)cl << jj, out->mpow[jj]);
+  transition(32L * cl, out->msb);
   return true;
+}
+
+bool sos_par_fill(const SosArgs& src, long T, SosPar* out) {
+  const long L = T + 2L * src.padlen;
+  if (L > 32L * kSosParMaxChunk) return false;
+  int cl = (int)((L + 31) / 32);
+  if ((cl & 1) == 0) ++cl;
+  return sos_par_fill_cl(src, cl, out);
 }
 
 // ---------------------------------------------------------------------------
@@ -111,6 +117,174 @@ cudaError_t sosfiltfilt_par_launch(const void* x, int x_is_f32, long rows, long 
                                    long group_stride, const SosPar& a, double* y, long ys, cudaStream_t st) {
   if (x_is_f32) return par_launch_t<float>((const float*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
   return par_launch_t<double>((const double*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+}
+
+// ---------------------------------------------------------------------------
+// long rows (e.g. the 360 001-frame trajectory of a one-hour recording): the row is cut into
+// super-blocks of 32 * CL samples, one warp each, and the state is carried across super-blocks
+// the same way it is carried across the lanes of a warp:
+//   1. STATE : every super-block's end state from a zero initial state (parallel),
+//   2. CARRY : s_in[b+1] = M_sb * s_in[b] + e0[b] along each row (one thread per row, n_sb steps),
+//   3. APPLY : every super-block again from its true initial state, writing the output (parallel);
+// once forward over the odd-extended input into a scratch row, once backward over that.
+// ---------------------------------------------------------------------------
+constexpr int kLongCL = 33;
+constexpr int kLongWarps = 4;
+
+template <typename TIn>
+__device__ __forceinline__ double odd_ext_elem(const TIn* __restrict__ xr, long T, int p, long i) {
+  const TIn two = (TIn)2;
+  if (i < p) return (double)(TIn)(two * xr[0] - xr[p - i]);
+  if (i < p + T) return (double)xr[i - p];
+  return (double)(TIn)(two * xr[T - 1] - xr[T - 2 - (i - p - T)]);
+}
+
+template <typename TIn, int NS, bool BWD, bool APPLY>
+__global__ void __launch_bounds__(kLongWarps * 32)
+    sos_long_kernel(const TIn* __restrict__ x, long x_row_stride, int group_rows, long group_stride,
+                    const double* __restrict__ fwd_in, long rows, long T, long n_sb, const __grid_constant__ SosPar a,
+                    const double* __restrict__ s_in, double* __restrict__ e0, double* __restrict__ fwd_out,
+                    double* __restrict__ y, long y_row_stride) {
+  extern __shared__ __align__(16) double sm_long[];
+  constexpr int D = 2 * NS;
+  constexpr int S = 32 * kLongCL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long unit = (long)blockIdx.x * kLongWarps + warp;
+  if (unit >= rows * n_sb) return;
+  const long row = unit / n_sb, sb = unit - row * n_sb;
+  const int p = a.padlen;
+  const long L = T + 2L * p;
+  double* buf = sm_long + (size_t)warp * S;
+  const long i0 = sb * S;  // first processing index of this super-block
+  const long g = row / group_rows, gi = row - g * group_rows;
+  const TIn* xr = x + g * group_stride + gi * x_row_stride;
+  const double* fr = fwd_in + row * L;
+  for (int j = lane; j < S; j += 32) {
+    const long i = i0 + j;
+    double v = 0.0;
+    if (i < L) v = BWD ? fr[L - 1 - i] : odd_ext_elem<TIn>(xr, T, p, i);
+    buf[j] = v;
+  }
+  __syncwarp();
+  const SosRegs<NS> c(a);
+  const int n_here = (int)min((long)S, L - i0);
+  double s0[D], z[D];
+  if (APPLY) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) s0[i] = s_in[unit * D + i];
+    warp_sos_core<NS, false, true>(buf, n_here, a, c, lane, s0, z);
+    for (int j = lane; j < n_here; j += 32) {
+      const long i = i0 + j;
+      if (BWD) {
+        const long e = L - 1 - i;
+        if (e >= p && e < p + T) y[row * y_row_stride + (e - p)] = buf[j];
+      } else {
+        fwd_out[row * L + i] = buf[j];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; ++i) s0[i] = 0.0;
+    warp_sos_core<NS, false, false>(buf, n_here, a, c, lane, s0, z);
+    if (lane == 31) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) e0[unit * D + i] = z[i];
+    }
+  }
+}
+
+template <typename TIn, int NS, bool BWD>
+__global__ void sos_long_carry_kernel(const TIn* __restrict__ x, long x_row_stride, int group_rows, long group_stride,
+                                      const double* __restrict__ fwd_in, long rows, long T, long n_sb,
+                                      const __grid_constant__ SosPar a, const double* __restrict__ e0,
+                                      double* __restrict__ s_in) {
+  constexpr int D = 2 * NS;
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int p = a.padlen;
+  const long L = T + 2L * p;
+  const long g = row / group_rows, gi = row - g * group_rows;
+  const double u0 = BWD ? fwd_in[row * L + L - 1] : odd_ext_elem<TIn>(x + g * group_stride + gi * x_row_stride, T, p, 0);
+  double s[D];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    s[2 * q] = a.zi[q][0] * u0;
+    s[2 * q + 1] = a.zi[q][1] * u0;
+  }
+  for (long b = 0; b < n_sb; ++b) {
+    const long unit = row * n_sb + b;
+    double nx[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      s_in[unit * D + r] = s[r];
+      double acc = e0[unit * D + r];
+#pragma unroll
+      for (int i = 0; i < D; ++i) acc = fma(a.msb[r][i], s[i], acc);
+      nx[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) s[r] = nx[r];
+  }
+}
+
+template <typename TIn, int NS>
+static cudaError_t long_launch_ns(const TIn* x, long rows, long T, long xs, int group_rows, long group_stride,
+                                  const SosPar& a, double* y, long ys, cudaStream_t st) {
+  constexpr int D = 2 * NS;
+  const long S = 32L * kLongCL, L = T + 2L * a.padlen, n_sb = (L + S - 1) / S;
+  const long units = rows * n_sb;
+  double *fwd = nullptr, *e0 = nullptr, *sin_ = nullptr;
+  cudaError_t e;
+  if ((e = cudaMallocAsync((void**)&fwd, (size_t)rows * L * 8, st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&e0, (size_t)units * D * 8, st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&sin_, (size_t)units * D * 8, st)) != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((units + kLongWarps - 1) / kLongWarps);
+  const unsigned cgrid = (unsigned)((rows + 63) / 64);
+  const size_t smem = (size_t)kLongWarps * S * 8;
+  sos_long_kernel<TIn, NS, false, false><<<grid, kLongWarps * 32, smem, st>>>(x, xs, group_rows, group_stride, fwd, rows,
+                                                                            T, n_sb, a, sin_, e0, fwd, y, ys);
+  sos_long_carry_kernel<TIn, NS, false><<<cgrid, 64, 0, st>>>(x, xs, group_rows, group_stride, fwd, rows, T, n_sb, a, e0,
+                                                              sin_);
+  sos_long_kernel<TIn, NS, false, true><<<grid, kLongWarps * 32, smem, st>>>(x, xs, group_rows, group_stride, fwd, rows,
+                                                                           T, n_sb, a, sin_, e0, fwd, y, ys);
+  sos_long_kernel<TIn, NS, true, false><<<grid, kLongWarps * 32, smem, st>>>(x, xs, group_rows, group_stride, fwd, rows,
+                                                                           T, n_sb, a, sin_, e0, fwd, y, ys);
+  sos_long_carry_kernel<TIn, NS, true><<<cgrid, 64, 0, st>>>(x, xs, group_rows, group_stride, fwd, rows, T, n_sb, a, e0,
+                                                             sin_);
+  sos_long_kernel<TIn, NS, true, true><<<grid, kLongWarps * 32, smem, st>>>(x, xs, group_rows, group_stride, fwd, rows, T,
+                                                                          n_sb, a, sin_, e0, fwd, y, ys);
+  count_launch(6);
+  e = cudaGetLastError();
+  cudaFreeAsync(fwd, st);
+  cudaFreeAsync(e0, st);
+  cudaFreeAsync(sin_, st);
+  return e;
+}
+
+template <typename TIn>
+static cudaError_t long_launch_t(const TIn* x, long rows, long T, long xs, int group_rows, long group_stride,
+                                 const SosPar& a, double* y, long ys, cudaStream_t st) {
+  switch (a.ns) {
+    case 1: return long_launch_ns<TIn, 1>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    case 2: return long_launch_ns<TIn, 2>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    case 3: return long_launch_ns<TIn, 3>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    case 4: return long_launch_ns<TIn, 4>(x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+bool sos_long_supported(const SosArgs& a, long rows, long T) {
+  const long L = T + 2L * a.padlen;
+  return a.n_sections >= 1 && a.n_sections <= kParMaxSections && L > 32L * kLongCL &&
+         rows * ((L + 32L * kLongCL - 1) / (32L * kLongCL)) < 0x7fffffffL * kLongWarps;
+}
+
+cudaError_t sosfiltfilt_long_launch(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
+                                    long group_stride, const SosArgs& src, double* y, long ys, cudaStream_t st) {
+  SosPar a;
+  if (!sos_par_fill_cl(src, kLongCL, &a)) return cudaErrorInvalidValue;
+  if (x_is_f32) return long_launch_t<float>((const float*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
+  return long_launch_t<double>((const double*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -90,6 +90,9 @@ struct SosPar;
 bool sos_par_fill(const SosArgs& src, long T, SosPar* out);
 cudaError_t sosfiltfilt_par_launch(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
                                    long group_stride, const SosPar& a, double* y, long ys, cudaStream_t st);
+bool sos_long_supported(const SosArgs& a, long rows, long T);
+cudaError_t sosfiltfilt_long_launch(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
+                                    long group_stride, const SosArgs& a, double* y, long ys, cudaStream_t st);
 bool change_fused_supported(const SosPar& a1, const SosPar* a2, int rows, long T, size_t* smem_out);
 cudaError_t change_fused_launch(const float* mfcc, long n_clips, int n_mfcc, int first, int rows, long T, int method,
                                 const SosPar& a1, const SosPar& a2, int out_kind, double* tot, size_t smem,

@@ -165,14 +165,205 @@ static cudaError_t launch_t(const float* mfcc, long n_clips, int n_coef, long T,
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Clip-resident variant: one CTA per (clip, chunk of windows).  The chunk's span of
+// every coefficient row is staged once in shared memory with coalesced loads (hop
+// windows overlap, so nothing is re-read), the magnitudes of a pass go back to
+// global memory as whole 4*(nfft/2+1)-byte rows, and the band energies are summed
+// over coefficients in shared memory -- no scattered global accesses, no atomics.
+// ---------------------------------------------------------------------------
+template <int NFFT>
+__global__ void __launch_bounds__(kModThreads, 2)
+    modspec_clip_kernel(const float* __restrict__ mfcc, int n_coef, long T, int win, int hop, long n_win, int wc,
+                        int n_chunks, int pitch, const float* __restrict__ hann, const float2* __restrict__ g_tw1,
+                        const float2* __restrict__ g_tw2, float* __restrict__ mag, float* __restrict__ band,
+                        const int* __restrict__ band_lo, const int* __restrict__ band_hi, int n_bands) {
+  using C = FftCfg<NFFT>;
+  static_assert(C::TPF <= 32, "one slot must fit in a warp");
+  constexpr int SLOTS = kModThreads / C::TPF;
+  constexpr int nb = NFFT / 2 + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_xb = reinterpret_cast<float2*>(smem_raw);             // [SLOTS][XBUF]
+  float2* s_tw1 = s_xb + SLOTS * C::XBUF;                         // [TW1]
+  float2* s_tw2 = s_tw1 + C::TW1;                                 // [TW2]
+  float* s_rows = reinterpret_cast<float*>(s_tw2 + C::TW2 + 1);   // [n_coef][pitch]
+  float* s_iband = s_rows + (size_t)n_coef * pitch;               // [wc * n_coef][n_bands]
+  float** s_dst = reinterpret_cast<float**>(s_iband + (((size_t)wc * n_coef * n_bands + 1) & ~(size_t)1));  // [SLOTS]
+  __shared__ int s_blo[16], s_bhi[16];
+  const int tid = threadIdx.x;
+  const int tau = tid % C::TPF, slot = tid / C::TPF;
+  const long clip = blockIdx.x / n_chunks;
+  const int chunk = (int)(blockIdx.x - clip * n_chunks);
+  const long w0 = (long)chunk * wc;
+  const int wca = (int)min((long)wc, n_win - w0);  // windows of this chunk
+  const int span = (wca - 1) * hop + win;
+
+  for (int i = tid; i < C::TW1; i += kModThreads) s_tw1[i] = g_tw1[i];
+  for (int i = tid; i < C::TW2; i += kModThreads) s_tw2[i] = g_tw2[i];
+  if (tid < 16) {
+    s_blo[tid] = tid < n_bands ? band_lo[tid] : 0;
+    s_bhi[tid] = tid < n_bands ? band_hi[tid] : 0;
+  }
+  for (int c = 0; c < n_coef; ++c) {
+    const float* src = mfcc + ((size_t)clip * n_coef + c) * T + w0 * hop;
+    for (int i = tid; i < span; i += kModThreads) s_rows[c * pitch + i] = __ldg(src + i);
+  }
+  float2 wreg[16];
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) {
+    const int c = tau + C::TPF * n2;
+    wreg[n2] = make_float2(0.5f * hann[2 * c], 0.5f * hann[2 * c + 1]);  // zero beyond win
+  }
+  float2 wtau;
+  sincospif(-2.0f * (float)tau / (float)NFFT, &wtau.y, &wtau.x);
+  __syncthreads();
+
+  float2* xb = s_xb + slot * C::XBUF;
+  float* pw = reinterpret_cast<float*>(xb);  // [nb] power of this slot's item, aliases the exchange buffer
+  const float inv_win = 1.0f / (float)win;
+  const int n_items = wca * n_coef;  // item = window * n_coef + coefficient
+  for (int base = 0; base < n_items; base += SLOTS) {
+    const int item = base + slot;
+    const bool valid = item < n_items;
+    const int w = valid ? item / n_coef : 0;
+    const int coef = valid ? item - w * n_coef : 0;
+    const float* src = s_rows + coef * pitch + w * hop;
+    float2 v[16];
+    float sum = 0.0f;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const int i0 = 2 * (tau + C::TPF * n2);
+      const float x0 = (valid && i0 < win) ? src[i0] : 0.0f;
+      const float x1 = (valid && i0 + 1 < win) ? src[i0 + 1] : 0.0f;
+      v[n2] = make_float2(x0, x1);
+      sum += x0 + x1;
+    }
+#pragma unroll
+    for (int o = C::TPF / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_win;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = make_float2((v[n2].x - mean) * wreg[n2].x, (v[n2].y - mean) * wreg[n2].y);
+
+    ph_pass1<NFFT>(v, s_tw1, tau);
+    __syncwarp();
+    ph_x1_write<NFFT>(v, xb, tau);
+    __syncwarp();
+    ph_x1_read<NFFT>(v, xb, tau);
+    ph_pass2<NFFT>(v, s_tw2, tau);
+    if constexpr (C::R3 > 1) {
+      __syncwarp();
+      ph_x2_write<NFFT>(v, xb, tau);
+      __syncwarp();
+      ph_x2_read<NFFT>(v, xb, tau);
+      ph_pass3<NFFT>(v);
+    }
+    __syncwarp();
+    ph_z_write<NFFT>(v, xb, tau);
+    __syncwarp();
+    float pwr[17];
+    {
+      int q = 0;
+      ph_split_smem_cb<NFFT>(xb, tau, wtau, [&](int, float p) { pwr[q++] = p; });
+    }
+    __syncwarp();
+    {
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int k = tau + C::TPF * r;
+        pw[k] = pwr[q++];
+        pw[C::M - k] = pwr[q++];
+      }
+      if (tau == 0) pw[C::M / 2] = pwr[16];
+    }
+    if (tau == 0)
+      s_dst[slot] = (mag != nullptr && valid) ? mag + (((size_t)clip * n_coef + coef) * n_win + w0 + w) * nb : nullptr;
+    __syncwarp();
+    if (band != nullptr) {  // (every lane takes part in the shuffles; invalid slots just do not store)
+      for (int b = 0; b < n_bands; ++b) {
+        float e = 0.0f;
+        for (int k = s_blo[b] + tau; k < s_bhi[b]; k += C::TPF) e += pw[k];
+#pragma unroll
+        for (int o = C::TPF / 2; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if (tau == 0 && valid) s_iband[(size_t)item * n_bands + b] = e;
+      }
+    }
+    __syncthreads();
+    // whole magnitude rows of this pass, coalesced
+    if (mag != nullptr) {
+      const int n_here = min(SLOTS, n_items - base);
+      for (int e = tid; e < n_here * nb; e += kModThreads) {
+        const int s2 = e / nb, k = e - s2 * nb;
+        float* d = s_dst[s2];
+        if (d != nullptr) d[k] = sqrtf(reinterpret_cast<const float*>(s_xb + s2 * C::XBUF)[k]);
+      }
+    }
+    __syncthreads();
+  }
+  if (band != nullptr) {
+    for (int e = tid; e < wca * n_bands; e += kModThreads) {
+      const int w = e / n_bands, b = e - w * n_bands;
+      float acc = 0.0f;
+      for (int c = 0; c < n_coef; ++c) acc += s_iband[((size_t)w * n_coef + c) * n_bands + b];
+      band[((size_t)clip * n_win + w0 + w) * n_bands + b] = acc;
+    }
+  }
+}
+
+template <int NFFT>
+static cudaError_t launch_clip_t(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, const float* hann,
+                                 const float2* tw1, const float2* tw2, float* mag, float* band, const int* lo,
+                                 const int* hi, int n_bands, cudaStream_t st, bool* handled) {
+  using C = FftCfg<NFFT>;
+  *handled = false;
+  if constexpr (C::TPF > 32) {
+    return cudaSuccess;
+  } else {
+    constexpr int SLOTS = kModThreads / C::TPF;
+    const long n_win = 1 + (T - win) / hop;
+    const int nbands = band != nullptr ? n_bands : 0;
+    // windows per chunk: rows + per-item band sums within ~100 KB so that two CTAs share an SM
+    const size_t fixed = (size_t)(SLOTS * C::XBUF + C::TW1 + C::TW2 + 1) * sizeof(float2) + SLOTS * sizeof(float*) + 64;
+    const size_t budget = 110 * 1024;
+    long wc = n_win;
+    auto need = [&](long w) {
+      const long span = (w - 1) * hop + win;
+      const long pitch = (span + 1) & ~1L;
+      return fixed + (size_t)n_coef * pitch * 4 + ((((size_t)w * n_coef * nbands) + 1) & ~(size_t)1) * 4;
+    };
+    if (need(1) > budget) return cudaSuccess;  // not handled: the generic kernel takes it
+    while (wc > 1 && need(wc) > budget) wc = (wc + 1) / 2;
+    while (wc < n_win && need(wc + 1) <= budget) ++wc;
+    const long n_chunks = (n_win + wc - 1) / wc;
+    if (n_clips * n_chunks > 0x7fffffffL) return cudaSuccess;
+    const long span = (wc - 1) * hop + win;
+    const int pitch = (int)((span + 1) & ~1L);
+    auto kfn = modspec_clip_kernel<NFFT>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    kfn<<<(unsigned)(n_clips * n_chunks), kModThreads, need(wc), st>>>(mfcc, n_coef, T, win, hop, n_win, (int)wc,
+                                                                        (int)n_chunks, pitch, hann, tw1, tw2, mag, band,
+                                                                        lo, hi, n_bands);
+    count_launch();
+    *handled = true;
+    return cudaGetLastError();
+  }
+}
+
 bool modspec_fast_supported(int nfft) { return nfft >= 32 && nfft <= 1024; }
 
 cudaError_t modspec_fast_launch(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, int nfft,
                                 const float* hann, const float2* tw1, const float2* tw2, float* mag, float* band,
                                 const int* lo, const int* hi, int n_bands, int sm_count, cudaStream_t st) {
   if (T < win) return cudaSuccess;
-#define MMF_MOD_CASE(N) \
-  case N: return launch_t<N>(mfcc, n_clips, n_coef, T, win, hop, hann, tw1, tw2, mag, band, lo, hi, n_bands, sm_count, st);
+#define MMF_MOD_CASE(N)                                                                                              \
+  case N: {                                                                                                          \
+    bool handled = false;                                                                                            \
+    cudaError_t e = launch_clip_t<N>(mfcc, n_clips, n_coef, T, win, hop, hann, tw1, tw2, mag, band, lo, hi, n_bands, \
+                                     st, &handled);                                                                  \
+    if (e != cudaSuccess || handled) return e;                                                                       \
+    return launch_t<N>(mfcc, n_clips, n_coef, T, win, hop, hann, tw1, tw2, mag, band, lo, hi, n_bands, sm_count, st); \
+  }
   switch (nfft) {
     MMF_MOD_CASE(32)
     MMF_MOD_CASE(64)

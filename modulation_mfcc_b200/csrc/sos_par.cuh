@@ -29,6 +29,7 @@ struct SosPar {
   double sos[kParMaxSections][6];  // a0-normalised rows b0 b1 b2 1 a1 a2
   double zi[kParMaxSections][2];   // sosfilt_zi
   double mpow[5][2 * kParMaxSections][2 * kParMaxSections];  // zero-input transition over CL * 2^j samples
+  double msb[2 * kParMaxSections][2 * kParMaxSections];      // ... over a whole super-block of 32 * CL samples
 };
 
 // cascade coefficients held in registers
@@ -60,10 +61,14 @@ __device__ __forceinline__ double sos_step(const SosRegs<NS>& c, double v, doubl
   return v;
 }
 
-// One direction over u[j] = REVERSE ? buf[L-1-j] : buf[j], j = 0..L-1, in place.
-// buf holds >= 32*CL doubles; all 32 lanes of the warp must call.
-template <int NS, bool REVERSE>
-__device__ __forceinline__ void warp_sos_pass(double* buf, int L, const SosPar& a, const SosRegs<NS>& c, int lane) {
+// One direction over u[j] = REVERSE ? buf[L-1-j] : buf[j], j = 0..L-1, from initial state s0
+// (meaningful on lane 0 only).  WRITE: outputs replace the inputs in place; otherwise only the
+// state after the last full chunk grid (32 * CL samples, zero padded) is produced.  On return
+// `z` holds the state at the end of this lane's chunk.  buf holds >= 32*CL doubles; all 32
+// lanes of the warp must call.
+template <int NS, bool REVERSE, bool WRITE>
+__device__ __forceinline__ void warp_sos_core(double* buf, int L, const SosPar& a, const SosRegs<NS>& c, int lane,
+                                              const double (&s0)[2 * NS], double (&z)[2 * NS]) {
   constexpr int D = 2 * NS;
   const int CL = a.CL;
   const int j0 = lane * CL;
@@ -71,17 +76,14 @@ __device__ __forceinline__ void warp_sos_pass(double* buf, int L, const SosPar& 
   // element j of the processing order lives at base[j * step]
   double* base = REVERSE ? buf + (L - 1 - j0) : buf + j0;
   constexpr int step = REVERSE ? -1 : 1;
-  const double u0 = buf[REVERSE ? L - 1 : 0];
-  double z[D];
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    z[2 * s] = lane == 0 ? a.zi[s][0] * u0 : 0.0;
-    z[2 * s + 1] = lane == 0 ? a.zi[s][1] * u0 : 0.0;
-  }
+  for (int i = 0; i < D; ++i) z[i] = lane == 0 ? s0[i] : 0.0;
   // 1. final state of this chunk from a zero (lane 0: true) initial state
 #pragma unroll 4
   for (int k = 0; k < n; ++k) sos_step<NS>(c, base[k * step], z);
-  // (chunks past the end of the row carry garbage through the scan; nothing real depends on them)
+  if (!WRITE)  // the carried state must cover the whole chunk grid: run the zero padding too
+    for (int k = n; k < CL; ++k) sos_step<NS>(c, 0.0, z);
+  // (WRITE: chunks past the end of the row carry garbage through the scan; nothing real depends on them)
   // 2. inclusive scan: z becomes the true state at the end of chunk `lane`
 #pragma unroll
   for (int jj = 0; jj < 5; ++jj) {
@@ -102,20 +104,33 @@ __device__ __forceinline__ void warp_sos_pass(double* buf, int L, const SosPar& 
       for (int r = 0; r < D; ++r) z[r] = zn[r];
     }
   }
-  // 3. true initial state of this chunk = end state of the previous one
-  double s[D];
+  if (WRITE) {
+    // 3. true initial state of this chunk = end state of the previous one
+    double s[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) s[i] = __shfl_up_sync(0xffffffffu, z[i], 1);
-  if (lane == 0) {
+    for (int i = 0; i < D; ++i) s[i] = __shfl_up_sync(0xffffffffu, z[i], 1);
+    if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < NS; ++q) {
-      s[2 * q] = a.zi[q][0] * u0;
-      s[2 * q + 1] = a.zi[q][1] * u0;
+      for (int i = 0; i < D; ++i) s[i] = s0[i];
     }
-  }
 #pragma unroll 4
-  for (int k = 0; k < n; ++k) base[k * step] = sos_step<NS>(c, base[k * step], s);
+    for (int k = 0; k < n; ++k) base[k * step] = sos_step<NS>(c, base[k * step], s);
+  }
   __syncwarp();
+}
+
+// scipy's start-up: state = zi * first sample of the processing order
+template <int NS, bool REVERSE>
+__device__ __forceinline__ void warp_sos_pass(double* buf, int L, const SosPar& a, const SosRegs<NS>& c, int lane) {
+  constexpr int D = 2 * NS;
+  const double u0 = buf[REVERSE ? L - 1 : 0];
+  double s0[D], z[D];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    s0[2 * q] = a.zi[q][0] * u0;
+    s0[2 * q + 1] = a.zi[q][1] * u0;
+  }
+  warp_sos_core<NS, REVERSE, true>(buf, L, a, c, lane, s0, z);
 }
 
 // forward + backward over the odd-extended row already sitting in buf[0..L)

@@ -190,12 +190,13 @@ def test_logmel_kernel_variants(name, flags, cuda_device):
         assert _mel_rel_err(lm[i], unclamped) <= LOGMEL_REL, (name, flags)
 
 
-@pytest.mark.parametrize("T", [22, 45, 333, 1001, 2001, 2038, 2039, 5000])
+@pytest.mark.parametrize("T", [22, 45, 333, 1001, 2001, 2038, 2039, 5000, 6071, 7000, 40000])
 @pytest.mark.parametrize("order", [2, 6, 8, 10])
 def test_sosfiltfilt_chunk_parallel_and_sequential_paths(T, order, cuda_device):
-    """Rows with T + 2*padlen <= 2080 and <= 4 sections take the chunk-parallel
-    kernel (one warp per row, exact state carry across 32 chunks); longer rows or
-    higher orders take the sequential kernel.  Both must equal scipy."""
+    """Rows with T + 2*padlen <= 6112 and <= 4 sections take the chunk-parallel
+    kernel (one warp per row, exact state carry across 32 chunks); longer rows the
+    super-block scan (state / carry / apply kernels); more than 4 sections the
+    sequential kernel.  All must equal scipy."""
     torch = _torch()
     rng = np.random.default_rng(100 + T + order)
     x = (rng.standard_normal((7, T)).cumsum(axis=-1) + 3.0).astype(np.float32)
