@@ -9,6 +9,7 @@
 // energies reduced over the warp with shuffles (all slots of a warp belong to the
 // same (clip, window) pair) followed by one atomicAdd per warp and band.
 #include <cfloat>
+#include <type_traits>
 
 #include "mmf_internal.h"
 #include "stft_core.cuh"
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(kModThreads)
   constexpr int SLOTS = kModThreads / C::TPF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_xb = reinterpret_cast<float2*>(smem_raw);  // [SLOTS][XBUF]
-  float2* s_tw1 = s_xb + SLOTS * C::XBUF;              // [TW1]
+  float2* s_tw1 = s_xb + SLOTS * C::XSTRIDE;              // [TW1]
   float2* s_tw2 = s_tw1 + C::TW1;                      // [TW2]
   __shared__ int s_blo[16], s_bhi[16];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(kModThreads)
   sincospif(-2.0f * (float)tau / (float)NFFT, &wtau.y, &wtau.x);
   __syncthreads();
 
-  float2* xb = s_xb + slot_in_block * C::XBUF;
+  float2* xb = s_xb + slot_in_block * C::XSTRIDE;
   const int nb = NFFT / 2 + 1;
   const float inv_win = 1.0f / (float)win;
   const long n_slots = n_pairs * cpad;
@@ -156,7 +157,7 @@ static cudaError_t launch_t(const float* mfcc, long n_clips, int n_coef, long T,
     cudaError_t e = cudaMemsetAsync(band, 0, (size_t)n_pairs * n_bands * sizeof(float), st);
     if (e != cudaSuccess) return e;
   }
-  const size_t smem = (size_t)(slots * C::XBUF + C::TW1 + C::TW2 + 1) * sizeof(float2);
+  const size_t smem = (size_t)(slots * C::XSTRIDE + C::TW1 + C::TW2 + 1) * sizeof(float2);
   cudaError_t ea = cudaFuncSetAttribute(modspec_fast_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (ea != cudaSuccess) return ea;
   modspec_fast_kernel<NFFT><<<(unsigned)blocks, kModThreads, smem, st>>>(mfcc, n_coef, T, win, hop, n_win, n_pairs, cpad,
@@ -172,23 +173,32 @@ static cudaError_t launch_t(const float* mfcc, long n_clips, int n_coef, long T,
 // global memory as whole 4*(nfft/2+1)-byte rows, and the band energies are summed
 // over coefficients in shared memory -- no scattered global accesses, no atomics.
 // ---------------------------------------------------------------------------
-template <int NFFT>
+// V = float2: one (window, coefficient) item per thread group; V = c2: two items per thread
+// group on packed FP32 instructions (fft_regs.cuh), which halves the passes.
+template <int NFFT, typename V>
 __global__ void __launch_bounds__(kModThreads, 2)
     modspec_clip_kernel(const float* __restrict__ mfcc, int n_coef, long T, int win, int hop, long n_win, int wc,
                         int n_chunks, int pitch, const float* __restrict__ hann, const float2* __restrict__ g_tw1,
                         const float2* __restrict__ g_tw2, float* __restrict__ mag, float* __restrict__ band,
                         const int* __restrict__ band_lo, const int* __restrict__ band_hi, int n_bands) {
   using C = FftCfg<NFFT>;
+  using TR = CxTraits<V>;
+  using Tw = typename TR::Tw;
+  using Xe = typename TR::Xe;
   static_assert(C::TPF <= 32, "one slot must fit in a warp");
+  constexpr int NI = TR::kFrames;  // items per thread group
   constexpr int SLOTS = kModThreads / C::TPF;
   constexpr int nb = NFFT / 2 + 1;
+  constexpr int PWP = (nb + 1) & ~1;  // floats per item in a slot's power area
+  static_assert(NI * PWP * 4 <= C::XBUF * 8, "power rows must fit in the exchange buffer of the slot");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* s_xb = reinterpret_cast<float2*>(smem_raw);             // [SLOTS][XBUF]
-  float2* s_tw1 = s_xb + SLOTS * C::XBUF;                         // [TW1]
-  float2* s_tw2 = s_tw1 + C::TW1;                                 // [TW2]
-  float* s_rows = reinterpret_cast<float*>(s_tw2 + C::TW2 + 1);   // [n_coef][pitch]
-  float* s_iband = s_rows + (size_t)n_coef * pitch;               // [wc * n_coef][n_bands]
-  float** s_dst = reinterpret_cast<float**>(s_iband + (((size_t)wc * n_coef * n_bands + 1) & ~(size_t)1));  // [SLOTS]
+  Xe* s_xb = reinterpret_cast<Xe*>(smem_raw);                      // [SLOTS][XBUF]
+  Tw* s_tw1 = reinterpret_cast<Tw*>(s_xb + SLOTS * C::XSTRIDE);       // [TW1]
+  Tw* s_tw2 = s_tw1 + C::TW1;                                      // [TW2 + 1]
+  float2* s_win = reinterpret_cast<float2*>(s_tw2 + C::TW2 + 1);   // [M] half-scaled Hann pairs (zero beyond win)
+  float* s_rows = reinterpret_cast<float*>(s_win + C::M);          // [n_coef][pitch]
+  float* s_iband = s_rows + (size_t)n_coef * pitch;                // [wc * n_coef][n_bands]
+  float** s_dst = reinterpret_cast<float**>(s_iband + (((size_t)wc * n_coef * n_bands + 1) & ~(size_t)1));  // [SLOTS*NI]
   __shared__ int s_blo[16], s_bhi[16];
   const int tid = threadIdx.x;
   const int tau = tid % C::TPF, slot = tid / C::TPF;
@@ -198,104 +208,195 @@ __global__ void __launch_bounds__(kModThreads, 2)
   const int wca = (int)min((long)wc, n_win - w0);  // windows of this chunk
   const int span = (wca - 1) * hop + win;
 
-  for (int i = tid; i < C::TW1; i += kModThreads) s_tw1[i] = g_tw1[i];
-  for (int i = tid; i < C::TW2; i += kModThreads) s_tw2[i] = g_tw2[i];
+  for (int i = tid; i < C::TW1; i += kModThreads) s_tw1[i] = make_tw<V>(g_tw1[i]);
+  for (int i = tid; i < C::TW2; i += kModThreads) s_tw2[i] = make_tw<V>(g_tw2[i]);
+  for (int i = tid; i < C::M; i += kModThreads) s_win[i] = make_float2(0.5f * hann[2 * i], 0.5f * hann[2 * i + 1]);
   if (tid < 16) {
     s_blo[tid] = tid < n_bands ? band_lo[tid] : 0;
     s_bhi[tid] = tid < n_bands ? band_hi[tid] : 0;
   }
-  for (int c = 0; c < n_coef; ++c) {
-    const float* src = mfcc + ((size_t)clip * n_coef + c) * T + w0 * hop;
-    for (int i = tid; i < span; i += kModThreads) s_rows[c * pitch + i] = __ldg(src + i);
-  }
-  float2 wreg[16];
+  {
+    // stage the chunk's span of every coefficient row, two rows and four column blocks per step
+    // (eight independent loads in flight per thread, no integer division)
+    const float* src0 = mfcc + (size_t)clip * n_coef * T + w0 * hop;
+    for (int c = 0; c < n_coef; c += 2) {
+      const float* r0 = src0 + (size_t)c * T;
+      const bool has1 = c + 1 < n_coef;
+      const float* r1 = has1 ? r0 + T : r0;
+      for (int i = tid; i < span; i += 4 * kModThreads) {
+        float a[4], b[4];
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) {
-    const int c = tau + C::TPF * n2;
-    wreg[n2] = make_float2(0.5f * hann[2 * c], 0.5f * hann[2 * c + 1]);  // zero beyond win
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + u * kModThreads;
+          a[u] = ii < span ? __ldg(r0 + ii) : 0.0f;
+          b[u] = ii < span ? __ldg(r1 + ii) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ii = i + u * kModThreads;
+          if (ii < span) {
+            s_rows[c * pitch + ii] = a[u];
+            if (has1) s_rows[(c + 1) * pitch + ii] = b[u];
+          }
+        }
+      }
+    }
   }
-  float2 wtau;
-  sincospif(-2.0f * (float)tau / (float)NFFT, &wtau.y, &wtau.x);
+  Tw wtau;
+  {
+    float2 w;
+    sincospif(-2.0f * (float)tau / (float)NFFT, &w.y, &w.x);
+    wtau = make_tw<V>(w);
+  }
   __syncthreads();
 
-  float2* xb = s_xb + slot * C::XBUF;
-  float* pw = reinterpret_cast<float*>(xb);  // [nb] power of this slot's item, aliases the exchange buffer
+  Xe* xb = s_xb + slot * C::XSTRIDE;
+  float* pw = reinterpret_cast<float*>(xb);  // [NI][PWP] power of this slot's items, aliases the exchange buffer
   const float inv_win = 1.0f / (float)win;
   const int n_items = wca * n_coef;  // item = window * n_coef + coefficient
-  for (int base = 0; base < n_items; base += SLOTS) {
-    const int item = base + slot;
-    const bool valid = item < n_items;
-    const int w = valid ? item / n_coef : 0;
-    const int coef = valid ? item - w * n_coef : 0;
-    const float* src = s_rows + coef * pitch + w * hop;
-    float2 v[16];
-    float sum = 0.0f;
+  for (int base = 0; base < n_items; base += SLOTS * NI) {
+    int item[NI];
+    bool valid[NI];
+    float xs[NI][32];
+    float mean[NI];
+#pragma unroll
+    for (int q = 0; q < NI; ++q) {
+      item[q] = base + slot * NI + q;
+      valid[q] = item[q] < n_items;
+      const int w = valid[q] ? item[q] / n_coef : 0;
+      const int coef = valid[q] ? item[q] - w * n_coef : 0;
+      const float* src = s_rows + coef * pitch + w * hop;
+      float sum = 0.0f;
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) {
+        const int i0 = 2 * (tau + C::TPF * n2);
+        const float x0 = (valid[q] && i0 < win) ? src[i0] : 0.0f;
+        const float x1 = (valid[q] && i0 + 1 < win) ? src[i0 + 1] : 0.0f;
+        xs[q][2 * n2] = x0;
+        xs[q][2 * n2 + 1] = x1;
+        sum += x0 + x1;
+      }
+#pragma unroll
+      for (int o = C::TPF / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      mean[q] = sum * inv_win;
+      if (tau == 0)
+        s_dst[slot * NI + q] =
+            (mag != nullptr && valid[q]) ? mag + (((size_t)clip * n_coef + coef) * n_win + w0 + w) * nb : nullptr;
+    }
+    V v[16];
 #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) {
-      const int i0 = 2 * (tau + C::TPF * n2);
-      const float x0 = (valid && i0 < win) ? src[i0] : 0.0f;
-      const float x1 = (valid && i0 + 1 < win) ? src[i0 + 1] : 0.0f;
-      v[n2] = make_float2(x0, x1);
-      sum += x0 + x1;
+      const float2 wv = s_win[tau + C::TPF * n2];
+      if constexpr (NI == 1) {
+        v[n2] = make_float2((xs[0][2 * n2] - mean[0]) * wv.x, (xs[0][2 * n2 + 1] - mean[0]) * wv.y);
+      } else {
+        v[n2] = CxTraits<c2>::make(pmake((xs[0][2 * n2] - mean[0]) * wv.x, (xs[1][2 * n2] - mean[1]) * wv.x),
+                                   pmake((xs[0][2 * n2 + 1] - mean[0]) * wv.y, (xs[1][2 * n2 + 1] - mean[1]) * wv.y));
+      }
     }
-#pragma unroll
-    for (int o = C::TPF / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum * inv_win;
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = make_float2((v[n2].x - mean) * wreg[n2].x, (v[n2].y - mean) * wreg[n2].y);
 
     ph_pass1<NFFT>(v, s_tw1, tau);
-    __syncwarp();
-    ph_x1_write<NFFT>(v, xb, tau);
-    __syncwarp();
-    ph_x1_read<NFFT>(v, xb, tau);
+    if constexpr (TR::kXParts == 1) {
+      __syncwarp();
+      ph_x1_write<NFFT, 0>(v, xb, tau);
+      __syncwarp();
+      ph_x1_read<NFFT, 0>(v, xb, tau);
+    } else {
+      __syncwarp();
+      ph_x1_write<NFFT, 1>(v, xb, tau);
+      __syncwarp();
+      ph_x1_read<NFFT, 1>(v, xb, tau);
+      __syncwarp();
+      ph_x1_write<NFFT, 2>(v, xb, tau);
+      __syncwarp();
+      ph_x1_read<NFFT, 2>(v, xb, tau);
+    }
     ph_pass2<NFFT>(v, s_tw2, tau);
     if constexpr (C::R3 > 1) {
-      __syncwarp();
-      ph_x2_write<NFFT>(v, xb, tau);
-      __syncwarp();
-      ph_x2_read<NFFT>(v, xb, tau);
+      if constexpr (TR::kXParts == 1) {
+        __syncwarp();
+        ph_x2_write<NFFT, 0>(v, xb, tau);
+        __syncwarp();
+        ph_x2_read<NFFT, 0>(v, xb, tau);
+      } else {
+        __syncwarp();
+        ph_x2_write<NFFT, 1>(v, xb, tau);
+        __syncwarp();
+        ph_x2_read<NFFT, 1>(v, xb, tau);
+        __syncwarp();
+        ph_x2_write<NFFT, 2>(v, xb, tau);
+        __syncwarp();
+        ph_x2_read<NFFT, 2>(v, xb, tau);
+      }
       ph_pass3<NFFT>(v);
     }
-    __syncwarp();
-    ph_z_write<NFFT>(v, xb, tau);
-    __syncwarp();
-    float pwr[17];
-    {
-      int q = 0;
-      ph_split_smem_cb<NFFT>(xb, tau, wtau, [&](int, float p) { pwr[q++] = p; });
+    V za[9], zb[8];
+    if constexpr (TR::kXParts == 1) {
+      __syncwarp();
+      ph_z_write<NFFT, 0>(v, xb, tau);
+      __syncwarp();
+      ph_z_gather<NFFT, 0>(za, zb, xb, tau);
+    } else {
+      __syncwarp();
+      ph_z_write<NFFT, 1>(v, xb, tau);
+      __syncwarp();
+      ph_z_gather<NFFT, 1>(za, zb, xb, tau);
+      __syncwarp();
+      ph_z_write<NFFT, 2>(v, xb, tau);
+      __syncwarp();
+      ph_z_gather<NFFT, 2>(za, zb, xb, tau);
     }
-    __syncwarp();
+    __syncwarp();  // every thread of the slot has its Z pairs: the buffer becomes the power area
+    // power rows in natural bin order: pw[q * PWP + k]
     {
-      int q = 0;
+      V pr[9];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) pr[r] = split_pair(za[r], zb[r], w32(r), wtau);
+      pr[8] = split_pair(za[8], za[8], w32(8), wtau);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const int k = tau + C::TPF * r;
-        pw[k] = pwr[q++];
-        pw[C::M - k] = pwr[q++];
+        if constexpr (NI == 1) {
+          pw[k] = pr[r].x;
+          pw[C::M - k] = pr[r].y;
+        } else {
+          pw[k] = plo(pr[r].x);
+          pw[PWP + k] = phi(pr[r].x);
+          pw[C::M - k] = plo(pr[r].y);
+          pw[PWP + C::M - k] = phi(pr[r].y);
+        }
       }
-      if (tau == 0) pw[C::M / 2] = pwr[16];
+      if (tau == 0) {
+        if constexpr (NI == 1) {
+          pw[C::M / 2] = pr[8].x;
+        } else {
+          pw[C::M / 2] = plo(pr[8].x);
+          pw[PWP + C::M / 2] = phi(pr[8].x);
+        }
+      }
     }
-    if (tau == 0)
-      s_dst[slot] = (mag != nullptr && valid) ? mag + (((size_t)clip * n_coef + coef) * n_win + w0 + w) * nb : nullptr;
     __syncwarp();
-    if (band != nullptr) {  // (every lane takes part in the shuffles; invalid slots just do not store)
-      for (int b = 0; b < n_bands; ++b) {
-        float e = 0.0f;
-        for (int k = s_blo[b] + tau; k < s_bhi[b]; k += C::TPF) e += pw[k];
+    if (band != nullptr) {  // (every lane takes part in the shuffles; invalid items just do not store)
 #pragma unroll
-        for (int o = C::TPF / 2; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-        if (tau == 0 && valid) s_iband[(size_t)item * n_bands + b] = e;
-      }
+      for (int q = 0; q < NI; ++q)
+        for (int b = 0; b < n_bands; ++b) {
+          float e = 0.0f;
+          for (int k = s_blo[b] + tau; k < s_bhi[b]; k += C::TPF) e += pw[q * PWP + k];
+#pragma unroll
+          for (int o = C::TPF / 2; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+          if (tau == 0 && valid[q]) s_iband[(size_t)item[q] * n_bands + b] = e;
+        }
     }
     __syncthreads();
-    // whole magnitude rows of this pass, coalesced
+    // whole magnitude rows of this pass: one warp per row, consecutive lanes -> consecutive bins
     if (mag != nullptr) {
-      const int n_here = min(SLOTS, n_items - base);
-      for (int e = tid; e < n_here * nb; e += kModThreads) {
-        const int s2 = e / nb, k = e - s2 * nb;
-        float* d = s_dst[s2];
-        if (d != nullptr) d[k] = sqrtf(reinterpret_cast<const float*>(s_xb + s2 * C::XBUF)[k]);
+      const int n_here = min(SLOTS * NI, n_items - base);
+      const int lane = tid & 31;
+      for (int it = tid >> 5; it < n_here; it += kModThreads / 32) {
+        float* d = s_dst[it];
+        const float* src = reinterpret_cast<const float*>(s_xb + (it / NI) * C::XSTRIDE) + (it % NI) * PWP;
+        if (d != nullptr)
+          for (int k = lane; k < nb; k += 32) d[k] = sqrtf(src[k]);
       }
     }
     __syncthreads();
@@ -320,10 +421,16 @@ static cudaError_t launch_clip_t(const float* mfcc, long n_clips, int n_coef, lo
     return cudaSuccess;
   } else {
     constexpr int SLOTS = kModThreads / C::TPF;
+    constexpr int nb = NFFT / 2 + 1;
+    // two items per thread group (packed FP32) when both power rows fit in the slot's exchange buffer
+    constexpr bool kPacked = 2 * ((nb + 1) & ~1) * 4 <= C::XBUF * 8;
+    using V = typename std::conditional<kPacked, c2, float2>::type;
+    constexpr int NI = kPacked ? 2 : 1;
     const long n_win = 1 + (T - win) / hop;
     const int nbands = band != nullptr ? n_bands : 0;
-    // windows per chunk: rows + per-item band sums within ~100 KB so that two CTAs share an SM
-    const size_t fixed = (size_t)(SLOTS * C::XBUF + C::TW1 + C::TW2 + 1) * sizeof(float2) + SLOTS * sizeof(float*) + 64;
+    // windows per chunk: rows + per-item band sums within ~110 KB so that two CTAs share an SM
+    const size_t fixed = (size_t)SLOTS * C::XSTRIDE * 8 + (size_t)(C::TW1 + C::TW2 + 1) * sizeof(typename CxTraits<V>::Tw) +
+                         (size_t)C::M * 8 + (size_t)SLOTS * NI * sizeof(float*) + 64;
     const size_t budget = 110 * 1024;
     long wc = n_win;
     auto need = [&](long w) {
@@ -338,7 +445,7 @@ static cudaError_t launch_clip_t(const float* mfcc, long n_clips, int n_coef, lo
     if (n_clips * n_chunks > 0x7fffffffL) return cudaSuccess;
     const long span = (wc - 1) * hop + win;
     const int pitch = (int)((span + 1) & ~1L);
-    auto kfn = modspec_clip_kernel<NFFT>;
+    auto kfn = modspec_clip_kernel<NFFT, V>;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     kfn<<<(unsigned)(n_clips * n_chunks), kModThreads, need(wc), st>>>(mfcc, n_coef, T, win, hop, n_win, (int)wc,

@@ -49,17 +49,19 @@ __global__ void __launch_bounds__(kMfccThreads)
   for (int j = 0; j < NC; ++j) acc[j] = 0.0f;
   if (valid) {
     float* col = logmel + (size_t)clip * n_mels * T + t;
-    // 8 independent loads in flight per thread before their FMAs (the kernel is a
-    // pure stream: 4*n_mels bytes in, 8*n_mfcc bytes out per frame)
-    for (int m0 = 0; m0 < n_mels; m0 += 8) {
-      float xv[8];
+    // software pipeline: the next 8 mel rows are in flight while the current 8 feed their FMAs
+    // (the kernel is a pure stream: 4*n_mels bytes in, 8*n_mfcc bytes out per frame)
+    float cur[8], nxt[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) xv[u] = (m0 + u < n_mels) ? __ldcs(col + (size_t)(m0 + u) * T) : 0.0f;
+    for (int u = 0; u < 8; ++u) cur[u] = (u < n_mels) ? __ldcs(col + (size_t)u * T) : 0.0f;
+    for (int m0 = 0; m0 < n_mels; m0 += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nxt[u] = (m0 + 8 + u < n_mels) ? __ldcs(col + (size_t)(m0 + 8 + u) * T) : 0.0f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int m = m0 + u;
         if (m < n_mels) {
-          const float x = fmaxf(xv[u], thr);
+          const float x = fmaxf(cur[u], thr);
           if (clamp_in_place && own) col[(size_t)m * T] = x;
           const float4* d4 = reinterpret_cast<const float4*>(s_dct + m * NC);
 #pragma unroll
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(kMfccThreads)
           }
         }
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
     }
   }
   if (own) {

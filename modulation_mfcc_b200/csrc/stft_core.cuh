@@ -45,6 +45,10 @@ struct FftCfg {
   static constexpr int X2 = R3 > 1 ? 16 * R3 * PITCH2 : 0;
   static constexpr int XZ = M;                // natural-order Z for the split step
   static constexpr int XBUF = (X1 > X2 ? (X1 > XZ ? X1 : XZ) : (X2 > XZ ? X2 : XZ));  // float2 per frame slot
+  // distance between the exchange buffers of consecutive thread groups (8-byte elements): with
+  // fewer than 16 threads per group several groups share a half-warp, and a stride that is a
+  // multiple of 16 elements would put all of them on the same banks
+  static constexpr int XSTRIDE = TPF >= 16 ? XBUF : XBUF + ((TPF % 16) - (XBUF % 16) + 16) % 16;
   static constexpr int TW1 = 16 * TPF;        // float2: W_M^{n1*k2} at [k2*TPF + n1]
   static constexpr int TW2 = 16 * R3;         // float2: W_TPF^{m1*j2} at [j2*R3 + m1]
 };

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   float* s_ptile = s_span + p.span_bufs * p.span_alloc;                     // [pt_bufs][F*ppitch]
   constexpr int FP = (C::F + 7) & ~7;  // bin rows padded to the MMA K tile; the pad rows stay zero
   Xe* s_xb = reinterpret_cast<Xe*>(s_ptile + ((p.pt_bufs * FP * p.ppitch + 3) & ~3));  // [SLOTS][XBUF]
-  Tw* s_tw1 = reinterpret_cast<Tw*>(s_xb + SLOTS * C::XBUF);                // [TW1]
+  Tw* s_tw1 = reinterpret_cast<Tw*>(s_xb + SLOTS * C::XSTRIDE);                // [TW1]
   Tw* s_tw2 = s_tw1 + C::TW1;                                               // [TW2]
   float2* s_win = reinterpret_cast<float2*>(s_tw2 + C::TW2);                // [M] half-scaled window pairs
   // mel tables: sparse FP32 walk            | tensor cores
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
 
     // ---------------- FFT phase: FPI frames per iteration ----------------
-    Xe* xb = s_xb + slot * C::XBUF;
+    Xe* xb = s_xb + slot * C::XSTRIDE;
     auto fsync = [] { frame_sync<C::TPF>(); };
     for (int fi = 0; fi < ((p.debug_skip & 1) ? 0 : p.TF / FPI); ++fi) {
       const int f = (fi * SLOTS + slot) * TR::kFrames;  // first (or only) frame of this thread group
@@ -457,7 +457,7 @@ static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_buf
   size_t b = 0;
   b += (size_t)span_bufs * span_alloc * 4;
   b += (size_t)((pt_bufs * FP * ppitch + 3) & ~3) * 4;
-  b += (size_t)SLOTS * C::XBUF * 8;
+  b += (size_t)SLOTS * C::XSTRIDE * 8;
   b += (size_t)(C::TW1 + C::TW2) * tw_bytes;
   b += (size_t)C::M * 8;
   b += (mel_tab_bytes + 15) & ~(size_t)15;
