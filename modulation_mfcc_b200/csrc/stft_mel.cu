@@ -62,12 +62,14 @@ __device__ __forceinline__ int float_key(float f) {
   return b >= 0 ? b : b ^ 0x7FFFFFFF;
 }
 
+// barrier over the TPF threads that transform one frame (pair): a warp-level sync when they
+// share a warp, otherwise a named barrier of their own (ids 1..15; id 0 is __syncthreads)
 template <int TPF>
-__device__ __forceinline__ void frame_sync() {
+__device__ __forceinline__ void frame_sync(int slot) {
   if constexpr (TPF <= 32) {
     __syncwarp();
   } else {
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(TPF) : "memory");
   }
 }
 
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 
     // ---------------- FFT phase: FPI frames per iteration ----------------
     Xe* xb = s_xb + slot * C::XSTRIDE;
-    auto fsync = [] { frame_sync<C::TPF>(); };
+    auto fsync = [slot] { frame_sync<C::TPF>(slot); };
     for (int fi = 0; fi < ((p.debug_skip & 1) ? 0 : p.TF / FPI); ++fi) {
       const int f = (fi * SLOTS + slot) * TR::kFrames;  // first (or only) frame of this thread group
       const int off = shift + lead + f * p.hop;
@@ -433,7 +435,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     // with two power-tile buffers no barrier is needed here: the next tile writes
     // the other buffer and the tile after that is separated by the next tile's
     // __syncthreads; with one buffer the readers must drain first
-    if (p.pt_bufs == 1) __syncthreads();
+    // One power-tile buffer: its readers must be done before the next tile's split step writes
+    // it.  The block barrier every tile already has before that point does the job: the one after
+    // the span loads (single span buffer, early prefetch) or the one after the plain loader's
+    // fill; only the remaining TMA modes need a barrier of their own here.
+    if (p.pt_bufs == 1 && p.use_tma && !(p.span_bufs == 1 && p.early_tma)) __syncthreads();
   }
 }
 
