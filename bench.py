@@ -356,7 +356,7 @@ def run_b200(args):
         },
         "gpu_launches": launches,
         "roofline": {
-            "kernel": "stft_mel_kernel<512>",
+            "kernel": "stft_mel_kernel<512, c2> (fused frame/window/rFFT/|X|^2/mel/log)",
             "bound": "hbm",
             "achieved": achieved,
             "peak": hbm_peak,
