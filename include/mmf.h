@@ -188,6 +188,26 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
                       const mmf_change_params* prm, const mmf_modspec_params* mod, double* tot_host, float* mfcc_host,
                       float* delta_host, float* mag_host, float* band_host);
 
+/* mmf_features_host for 16-bit PCM as it sits in a WAV file: the int16 samples cross PCIe as they are
+ * (half the bytes) and are scaled to float32 = x / 32768 on the device, exactly what
+ * librosa.load / soundfile does on the CPU before the path starts (script/mfcc.py:373). */
+int mmf_features_host_pcm16(mmf_plan* plan, const int16_t* pcm16_host, int64_t n_clips, int64_t n_samples,
+                            int64_t clip_stride, const mmf_change_params* prm, const mmf_modspec_params* mod,
+                            double* tot_host, float* mfcc_host, float* delta_host, float* mag_host,
+                            float* band_host);
+
+/* Device-side PCM16 -> float32 in [-1, 1): y = x / 32768 (script/mfcc.py:373, :284 decode step). */
+int mmf_pcm16_to_f32(mmf_plan* plan, const int16_t* pcm16_dev, int64_t n, float* pcm_dev, void* stream);
+
+/* Rational-rate polyphase resampler with scipy.signal.resample_poly / upfirdn semantics:
+ * y_full[m] = sum_i h[m*down - i*up] * x[i];  y = y_full[n_pre_remove : n_pre_remove + n_out].
+ * h (already scaled by `up` and zero-padded as resample_poly does) is designed on the host.  The
+ * step before the path: librosa.load(path, sr=sigSr) at script/mfcc.py:373, :284 (librosa uses
+ * soxr_hq there; this resampler is NOT bit-identical to it). */
+int mmf_resample_poly(mmf_plan* plan, const float* x_dev, int64_t n_clips, int64_t n_in, int64_t x_stride,
+                      const float* h_host, int32_t len_h, int32_t up, int32_t down, int64_t n_pre_remove, int64_t n_out,
+                      float* y_dev, int64_t y_stride, void* stream);
+
 /* Same as mmf_features_host with only totChange (and optionally MFCC) returned:
  * HOST buffers in and out (the call the Python drop-in makes for a numpy
  * array): copies PCM host->device in chunks overlapped with compute, runs the

@@ -251,34 +251,44 @@ def applyFilter(x, sr, /, *, filt="iir", cutOff=[None], filtLen=6, filtType="low
 # ---------------------------------------------------------------------------
 
 
-def _read_audio(path: str, sr: float):
+def _read_audio(path: str, sr: float, device=None):
     """Decode a WAV file to float32 in [-1, 1] shaped [channels, n] or [n] and bring
     it to ``sr`` (librosa.load(path, sr=sr, mono=False) at script/mfcc.py:373).
 
-    Decode/resample sits *before* the measured path; it
-    uses scipy's WAV reader and a polyphase resampler on the host, which is not
-    bit-identical to librosa's soxr_hq resampler."""
+    Decode/resample sits *before* the measured path.
+    The file is parsed on the host (scipy's WAV reader); 16-bit PCM is scaled on the
+    device (``mmf_pcm16_to_f32``) and the rate conversion is a polyphase resampler on
+    the device (``mmf_resample_poly``, scipy.signal.resample_poly semantics).  librosa
+    resamples with soxr_hq: same band limits, not bit-identical."""
     from scipy.io import wavfile
 
+    torch = _torch()
     file_sr, data = wavfile.read(path)
-    if data.dtype == np.int16:
-        y = data.astype(np.float32) / 32768.0
-    elif data.dtype == np.int32:
-        y = (data.astype(np.float64) / 2147483648.0).astype(np.float32)
-    elif data.dtype == np.uint8:
-        y = (data.astype(np.float32) - 128.0) / 128.0
-    else:
-        y = data.astype(np.float32)
-    if y.ndim == 2:
-        y = y.T
-        if y.shape[0] == 1:
-            y = y[0]
-    if sr is not None and float(file_sr) != float(sr):
-        from fractions import Fraction
+    if data.ndim == 2:
+        data = data.T
+        if data.shape[0] == 1:
+            data = data[0]
+    data = np.ascontiguousarray(data)
+    plan = _any_plan(_device_index(device))
+    try:
+        if data.dtype == np.int16:
+            y = plan.pcm16_to_f32(data)
+        else:
+            if data.dtype == np.int32:
+                host = (data.astype(np.float64) / 2147483648.0).astype(np.float32)
+            elif data.dtype == np.uint8:
+                host = (data.astype(np.float32) - 128.0) / 128.0
+            else:
+                host = data.astype(np.float32)
+            y = _to_dev(host, torch.float32, plan.cfg.device)
+        if sr is not None and float(file_sr) != float(sr):
+            from fractions import Fraction
 
-        fr = Fraction(float(sr) / float(file_sr)).limit_denominator(1000)
-        y = scipy.signal.resample_poly(y, fr.numerator, fr.denominator, axis=-1).astype(np.float32)
-    return np.ascontiguousarray(y)
+            fr = Fraction(float(sr) / float(file_sr)).limit_denominator(1000)
+            y = plan.resample_poly(y, fr.numerator, fr.denominator)
+    except MmfError as e:
+        _raise_from(e)
+    return np.ascontiguousarray(y.cpu().numpy())
 
 
 def load_channel(file_path: str, signal_sample_rate: float = 10_000, channel_nb: int = 0):

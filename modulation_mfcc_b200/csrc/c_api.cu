@@ -77,6 +77,7 @@ static void* carve(unsigned char*& cur, size_t bytes) {
 
 static int fill_sos(const double* sos, int n_sections, SosArgs* a) {
   if (n_sections < 1 || n_sections > 16) return fail(MMF_ERR_UNSUPPORTED, "n_sections must be in [1, 16]");
+  std::memset(a, 0, sizeof(*a));  // (also the padding: the struct is used as a cache key)
   a->n_sections = n_sections;
   std::memset(a->sos, 0, sizeof(a->sos));
   std::memset(a->zi, 0, sizeof(a->zi));
@@ -871,10 +872,16 @@ int mmf_change_from_logmel(mmf_plan* plan, float* logmel_dev, const int32_t* cli
                   (cudaStream_t)stream);
 }
 
-int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
-                      const mmf_change_params* prm, const mmf_modspec_params* mod, double* tot_host, float* mfcc_host,
-                      float* delta_host, float* mag_host, float* band_host) {
-  if (!plan || !pcm_host || !prm || !tot_host) return fail(MMF_ERR_INVALID, "NULL argument");
+}  // extern "C"
+
+// pcm_host: float32 samples, or (pcm16 != 0) int16 samples converted on the device
+static int features_host_impl(mmf_plan* plan, const void* pcm_host_v, int pcm16, int64_t n_clips, int64_t n_samples,
+                              int64_t clip_stride, const mmf_change_params* prm, const mmf_modspec_params* mod,
+                              double* tot_host, float* mfcc_host, float* delta_host, float* mag_host,
+                              float* band_host) {
+  const float* pcm_host = (const float*)pcm_host_v;
+  const int16_t* pcm_host16 = (const int16_t*)pcm_host_v;
+  if (!plan || !pcm_host_v || !prm || !tot_host) return fail(MMF_ERR_INVALID, "NULL argument");
   if (n_clips < 1 || n_samples < 1) return fail(MMF_ERR_INVALID, "n_clips and n_samples must be positive");
   if ((mag_host || band_host) && !mod) return fail(MMF_ERR_INVALID, "modulation outputs requested without parameters");
   MMF_CUDA(cudaSetDevice(plan->cfg.device));
@@ -904,7 +911,8 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
   const size_t mag_slot = (want_mod && mag_host) ? align_up((size_t)chunk * c.n_mfcc * n_win * nbins * 4, 256) : 0;
   const size_t band_slot = (want_mod && band_host) ? align_up((size_t)chunk * n_win * mod->n_bands * 4 + 4, 256) : 0;
   const size_t change_slot = change_ws_bytes(plan, chunk, T, true, !need_mfcc_dev, rows);
-  const size_t slot = pcm_slot + tot_slot + mfcc_slot + delta_slot + mag_slot + band_slot + change_slot;
+  const size_t raw_slot = pcm16 ? align_up((size_t)chunk * n_samples * 2, 256) : 0;  // int16 staging
+  const size_t slot = pcm_slot + raw_slot + tot_slot + mfcc_slot + delta_slot + mag_slot + band_slot + change_slot;
   int rc = ensure_ws(plan, (64 << 10) + 2 * slot);
   if (rc) return rc;
   int64_t done = 0;
@@ -915,6 +923,8 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
     unsigned char* cur = (unsigned char*)plan->ws + (64 << 10) + (size_t)s * slot;
     float* d_pcm = (float*)cur;
     cur += pcm_slot;
+    int16_t* d_raw = pcm16 ? (int16_t*)cur : nullptr;
+    cur += raw_slot;
     double* d_tot = (double*)cur;
     cur += tot_slot;
     float* d_mfcc = need_mfcc_dev ? (float*)cur : nullptr;
@@ -926,7 +936,18 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
     float* d_band = band_slot ? (float*)cur : nullptr;
     cur += band_slot;
     // stream order serialises reuse of slot s (chunk i-2 ran on the same stream)
-    if (clip_stride == n_samples) {
+    if (pcm16) {
+      if (clip_stride == n_samples) {
+        MMF_CUDA(cudaMemcpyAsync(d_raw, pcm_host16 + (size_t)done * clip_stride, (size_t)nc * n_samples * 2,
+                                 cudaMemcpyHostToDevice, st));
+      } else {
+        MMF_CUDA(cudaMemcpy2DAsync(d_raw, (size_t)n_samples * 2, pcm_host16 + (size_t)done * clip_stride,
+                                   (size_t)clip_stride * 2, (size_t)n_samples * 2, (size_t)nc, cudaMemcpyHostToDevice,
+                                   st));
+      }
+      cudaError_t ce = pcm16_to_f32_launch(d_raw, (long)nc * n_samples, d_pcm, st);
+      if (ce != cudaSuccess) return cuda_fail(ce, "pcm16_to_f32_kernel launch");
+    } else if (clip_stride == n_samples) {
       MMF_CUDA(cudaMemcpyAsync(d_pcm, pcm_host + (size_t)done * clip_stride, (size_t)nc * n_samples * 4,
                                cudaMemcpyHostToDevice, st));
     } else {
@@ -958,6 +979,49 @@ int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, in
   }
   MMF_CUDA(cudaStreamSynchronize(plan->streams[0]));
   MMF_CUDA(cudaStreamSynchronize(plan->streams[1]));
+  return MMF_OK;
+}
+
+extern "C" {
+
+int mmf_features_host(mmf_plan* plan, const float* pcm_host, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
+                      const mmf_change_params* prm, const mmf_modspec_params* mod, double* tot_host, float* mfcc_host,
+                      float* delta_host, float* mag_host, float* band_host) {
+  return features_host_impl(plan, pcm_host, 0, n_clips, n_samples, clip_stride, prm, mod, tot_host, mfcc_host,
+                            delta_host, mag_host, band_host);
+}
+
+int mmf_features_host_pcm16(mmf_plan* plan, const int16_t* pcm16_host, int64_t n_clips, int64_t n_samples,
+                            int64_t clip_stride, const mmf_change_params* prm, const mmf_modspec_params* mod,
+                            double* tot_host, float* mfcc_host, float* delta_host, float* mag_host,
+                            float* band_host) {
+  return features_host_impl(plan, pcm16_host, 1, n_clips, n_samples, clip_stride, prm, mod, tot_host, mfcc_host,
+                            delta_host, mag_host, band_host);
+}
+
+int mmf_pcm16_to_f32(mmf_plan* plan, const int16_t* pcm16_dev, int64_t n, float* pcm_dev, void* stream) {
+  if (!plan || !pcm16_dev || !pcm_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n < 1) return fail(MMF_ERR_INVALID, "n must be positive");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  cudaError_t e = pcm16_to_f32_launch(pcm16_dev, n, pcm_dev, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "pcm16_to_f32_kernel launch");
+  return MMF_OK;
+}
+
+int mmf_resample_poly(mmf_plan* plan, const float* x_dev, int64_t n_clips, int64_t n_in, int64_t x_stride,
+                      const float* h_host, int32_t len_h, int32_t up, int32_t down, int64_t n_pre_remove, int64_t n_out,
+                      float* y_dev, int64_t y_stride, void* stream) {
+  if (!plan || !x_dev || !h_host || !y_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_clips < 1 || n_clips > 65535 || n_in < 1 || n_out < 1) return fail(MMF_ERR_INVALID, "bad sizes");
+  if (up < 1 || down < 1 || len_h < 1 || (size_t)len_h * 4 > (60u << 10))
+    return fail(MMF_ERR_UNSUPPORTED, "need up, down >= 1 and a filter of at most 15360 taps");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  void* h_dev = nullptr;
+  int rc = stage_consts(plan, h_host, (size_t)len_h * 4, 0, &h_dev, (cudaStream_t)stream);
+  if (rc) return rc;
+  cudaError_t e = resample_poly_launch(x_dev, n_clips, n_in, x_stride, (const float*)h_dev, len_h, up, down,
+                                       n_pre_remove, n_out, y_stride, y_dev, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "resample_poly_kernel launch");
   return MMF_OK;
 }
 

@@ -10,6 +10,7 @@
 //    float64 intermediates (96 KB per 10 s clip) never touch HBM.
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "mmf_internal.h"
 #include "sos_par.cuh"
@@ -40,17 +41,47 @@ static bool sos_par_fill_cl(const SosArgs& src, int cl, SosPar* out) {
     out->zi[s][1] = src.zi[s][1];
   }
   const int D = 2 * src.n_sections;
-  // zero-input transition over `steps` samples, column by column
-  auto transition = [&](long steps, double (*m)[2 * kParMaxSections]) {
-    for (int c = 0; c < D; ++c) {
-      double z[2 * kParMaxSections] = {0};
-      z[c] = 1.0;
-      for (long i = 0; i < steps; ++i) host_sos_step(*out, 0.0, z);
-      for (int r = 0; r < D; ++r) m[r][c] = z[r];
-    }
+  // zero-input transition over one chunk (cl samples), column by column ...
+  for (int c = 0; c < D; ++c) {
+    double z[2 * kParMaxSections] = {0};
+    z[c] = 1.0;
+    for (int i = 0; i < cl; ++i) host_sos_step(*out, 0.0, z);
+    for (int r = 0; r < D; ++r) out->mpow[0][r][c] = z[r];
+  }
+  // ... and over 2, 4, 8, 16 chunks and the whole super-block (32 chunks) by repeated squaring
+  auto square = [&](const double (*a)[2 * kParMaxSections], double (*m)[2 * kParMaxSections]) {
+    for (int r = 0; r < D; ++r)
+      for (int c = 0; c < D; ++c) {
+        double acc = 0.0;
+        for (int k = 0; k < D; ++k) acc = std::fma(a[r][k], a[k][c], acc);
+        m[r][c] = acc;
+      }
   };
-  for (int jj = 0; jj < 5; ++jj) transition((long)cl << jj, out->mpow[jj]);
-  transition(32L * cl, out->msb);
+  for (int jj = 1; jj < 5; ++jj) square(out->mpow[jj - 1], out->mpow[jj]);
+  square(out->mpow[4], out->msb);
+  return true;
+}
+
+// the tables depend only on (cascade, chunk length): keep the last few per thread
+static bool sos_par_cached(const SosArgs& src, int cl, SosPar* out) {
+  struct Entry {
+    SosArgs key;
+    int cl;
+    SosPar par;
+  };
+  static thread_local std::vector<Entry> cache;
+  for (const Entry& e : cache)
+    if (e.cl == cl && std::memcmp(&e.key, &src, sizeof(SosArgs)) == 0) {
+      *out = e.par;
+      return true;
+    }
+  if (!sos_par_fill_cl(src, cl, out)) return false;
+  if (cache.size() >= 16) cache.erase(cache.begin());
+  Entry e;
+  std::memcpy(&e.key, &src, sizeof(SosArgs));
+  e.cl = cl;
+  e.par = *out;
+  cache.push_back(e);
   return true;
 }
 
@@ -59,7 +90,7 @@ bool sos_par_fill(const SosArgs& src, long T, SosPar* out) {
   if (L > 32L * kSosParMaxChunk) return false;
   int cl = (int)((L + 31) / 32);
   if ((cl & 1) == 0) ++cl;
-  return sos_par_fill_cl(src, cl, out);
+  return sos_par_cached(src, cl, out);
 }
 
 // ---------------------------------------------------------------------------
@@ -94,8 +125,7 @@ static cudaError_t par_launch_ns(const TIn* x, long rows, long T, long xs, int g
   const unsigned grid = (unsigned)((rows + kParWarps - 1) / kParWarps);
   const size_t smem = (size_t)kParWarps * 32 * a.CL * sizeof(double);
   auto kfn = sosfiltfilt_par_kernel<TIn, NS>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return e;
+  MMF_SMEM_ONCE(kfn, 200 * 1024);
   kfn<<<grid, kParWarps * 32, smem, st>>>(x, rows, (int)T, xs, group_rows, group_stride, a, y, ys);
   count_launch();
   return cudaGetLastError();
@@ -282,7 +312,7 @@ bool sos_long_supported(const SosArgs& a, long rows, long T) {
 cudaError_t sosfiltfilt_long_launch(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
                                     long group_stride, const SosArgs& src, double* y, long ys, cudaStream_t st) {
   SosPar a;
-  if (!sos_par_fill_cl(src, kLongCL, &a)) return cudaErrorInvalidValue;
+  if (!sos_par_cached(src, kLongCL, &a)) return cudaErrorInvalidValue;
   if (x_is_f32) return long_launch_t<float>((const float*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
   return long_launch_t<double>((const double*)x, rows, T, xs, group_rows, group_stride, a, y, ys, st);
 }
@@ -386,8 +416,7 @@ static cudaError_t fused_launch_cl(const float* mfcc, long n_clips, int n_mfcc, 
   // >= ceil(T / (32*kFusedPerThread)) warps for the derivative phase, one per row if possible
   const int warps = std::min(kFusedMaxWarps, std::max(rows, (int)((T + 32 * kFusedPerThread - 1) / (32 * kFusedPerThread))));
   auto kfn = change_fused_kernel<NS1, NS2>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  if (e != cudaSuccess) return e;
+  MMF_SMEM_ONCE(kfn, 220 * 1024);
   kfn<<<(unsigned)n_clips, warps * 32, smem, st>>>(mfcc, n_mfcc, first, rows, (int)T, method, a1, a2, out_kind, tot);
   count_launch();
   return cudaGetLastError();

@@ -113,6 +113,10 @@ cudaError_t modspec_fast_launch(const float* mfcc, long n_clips, int n_coef, lon
 cudaError_t rms_launch(const float* pcm, long n_clips, long n, long stride, int frame_length, int hop, int pad,
                        long T, float* out, cudaStream_t st);
 cudaError_t fill_i32_launch(int* p, long n, int v, cudaStream_t st);
+cudaError_t pcm16_to_f32_launch(const int16_t* x, long n, float* y, cudaStream_t st);
+cudaError_t resample_poly_launch(const float* x, long n_clips, long n_in, long x_stride, const float* h_dev, int len_h,
+                                 int up, int down, long n_pre_remove, long n_out, long y_stride, float* y,
+                                 cudaStream_t st);
 
 // ---- host tables (host_tables.cpp)
 struct MelSparse {
@@ -127,6 +131,19 @@ bool host_mel_sparse(const std::vector<float>& mel, const std::vector<double>& m
 void host_dct(int n_mfcc, int n_mels, std::vector<float>& d);
 void host_twiddles(int n_fft, const StftGeometry& g, std::vector<float2>& tw1, std::vector<float2>& tw2);
 int host_sos_zi(const double* sos, int n_sections, double* zi, int* padlen);
+
+// opt a kernel into large dynamic shared memory once per device instead of on every launch
+#define MMF_SMEM_ONCE(kfn, bytes)                                                                        \
+  do {                                                                                                   \
+    static bool done__[64] = {};                                                                         \
+    int dev__ = 0;                                                                                       \
+    cudaGetDevice(&dev__);                                                                               \
+    if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                                    \
+      cudaError_t e__ = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)); \
+      if (e__ != cudaSuccess) return e__;                                                                \
+      if (dev__ >= 0 && dev__ < 64) done__[dev__] = true;                                                \
+    }                                                                                                    \
+  } while (0)
 
 void set_error(const std::string& msg);
 void count_launch(int n = 1);

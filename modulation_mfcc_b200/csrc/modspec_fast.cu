@@ -158,8 +158,7 @@ static cudaError_t launch_t(const float* mfcc, long n_clips, int n_coef, long T,
     if (e != cudaSuccess) return e;
   }
   const size_t smem = (size_t)(slots * C::XSTRIDE + C::TW1 + C::TW2 + 1) * sizeof(float2);
-  cudaError_t ea = cudaFuncSetAttribute(modspec_fast_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (ea != cudaSuccess) return ea;
+  MMF_SMEM_ONCE(modspec_fast_kernel<NFFT>, 200 * 1024);
   modspec_fast_kernel<NFFT><<<(unsigned)blocks, kModThreads, smem, st>>>(mfcc, n_coef, T, win, hop, n_win, n_pairs, cpad,
                                                                      hann, tw1, tw2, mag, band, lo, hi, n_bands);
   count_launch();
@@ -446,8 +445,7 @@ static cudaError_t launch_clip_t(const float* mfcc, long n_clips, int n_coef, lo
     const long span = (wc - 1) * hop + win;
     const int pitch = (int)((span + 1) & ~1L);
     auto kfn = modspec_clip_kernel<NFFT, V>;
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
+    MMF_SMEM_ONCE(kfn, 200 * 1024);
     kfn<<<(unsigned)(n_clips * n_chunks), kModThreads, need(wc), st>>>(mfcc, n_coef, T, win, hop, n_win, (int)wc,
                                                                         (int)n_chunks, pitch, hann, tw1, tw2, mag, band,
                                                                         lo, hi, n_bands);

@@ -121,8 +121,7 @@ cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const i
   size_t smem = ((size_t)n_mels * nc + (size_t)nc * (kMfccThreads + 1)) * sizeof(float);
 #define MMF_MFCC_CASE(N)                                                                                         \
   case N: {                                                                                                      \
-    cudaError_t e = cudaFuncSetAttribute(mfcc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-    if (e != cudaSuccess) return e;                                                                              \
+    MMF_SMEM_ONCE(mfcc_kernel<N>, 200 * 1024);                                                                   \
     mfcc_kernel<N><<<grid, kMfccThreads, smem, st>>>(dct_pad, nc_pad, logmel, clipmax, T, n_mels, n_mfcc, top_db, \
                                                      mfcc, delta, clamp_in_place);                               \
     break;                                                                                                       \
@@ -601,6 +600,71 @@ cudaError_t rms_launch(const float* pcm, long n_clips, long n, long stride, int 
   const int threads = 256;  // 8 frames per block
   dim3 grid((unsigned)((T + 7) / 8), (unsigned)n_clips);
   rms_kernel<<<grid, threads, 0, st>>>(pcm, n, stride, frame_length, hop, pad, T, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// PCM16 ingest: what librosa.load does to a 16-bit WAV before the path starts
+// (script/mfcc.py:373 -> soundfile -> float32 = int16 / 32768), on the device, so that
+// only 2 bytes per sample cross PCIe.  8 samples per thread, 128-bit accesses.
+// ---------------------------------------------------------------------------
+__global__ void pcm16_to_f32_kernel(const int16_t* __restrict__ x, long n, float* __restrict__ y) {
+  const long i8 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  constexpr float k = 1.0f / 32768.0f;
+  if (i8 + 8 <= n && (reinterpret_cast<uintptr_t>(x + i8) & 15) == 0 && (reinterpret_cast<uintptr_t>(y + i8) & 15) == 0) {
+    const int4 v = *reinterpret_cast<const int4*>(x + i8);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      o[2 * q] = (float)(short)(w[q] & 0xffff) * k;
+      o[2 * q + 1] = (float)(short)(w[q] >> 16) * k;
+    }
+    *reinterpret_cast<float4*>(y + i8) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(y + i8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  } else {
+    for (long i = i8; i < n && i < i8 + 8; ++i) y[i] = (float)x[i] * k;
+  }
+}
+
+cudaError_t pcm16_to_f32_launch(const int16_t* x, long n, float* y, cudaStream_t st) {
+  const long threads = (n + 7) / 8;
+  pcm16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, n, y);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Polyphase rational resampler: scipy.signal.resample_poly / upfirdn semantics,
+// y_full[m] = sum_i h[m*down - i*up] * x[i], then y = y_full[n_pre_remove : n_pre_remove + n_out]
+// (the step before the path: librosa.load(sr=sigSr) at script/mfcc.py:373, :284).
+// One thread per output sample, ~len(h)/up taps each, float64 accumulation.
+// ---------------------------------------------------------------------------
+__global__ void resample_poly_kernel(const float* __restrict__ x, long n_in, long x_stride, const float* __restrict__ h,
+                                     int len_h, int up, int down, long n_pre_remove, long n_out, long y_stride,
+                                     float* __restrict__ y) {
+  const long mo = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mo >= n_out) return;
+  const float* xr = x + (size_t)blockIdx.y * x_stride;
+  const long pos = (mo + n_pre_remove) * down;  // position in the zero-stuffed input
+  long i_hi = pos / up;                         // largest i with pos - i*up >= 0
+  if (i_hi > n_in - 1) i_hi = n_in - 1;
+  long i_lo = (pos - len_h + up) / up;          // smallest i with pos - i*up <= len_h - 1 (ceil for pos >= len_h - 1)
+  if (pos - len_h + 1 <= 0) i_lo = 0;
+  double acc = 0.0;
+  for (long i = i_lo; i <= i_hi; ++i) {
+    const long k = pos - i * up;
+    if (k >= 0 && k < len_h) acc = fma((double)h[k], (double)xr[i], acc);
+  }
+  y[(size_t)blockIdx.y * y_stride + mo] = (float)acc;
+}
+
+cudaError_t resample_poly_launch(const float* x, long n_clips, long n_in, long x_stride, const float* h_dev, int len_h,
+                                 int up, int down, long n_pre_remove, long n_out, long y_stride, float* y,
+                                 cudaStream_t st) {
+  dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)n_clips);
+  resample_poly_kernel<<<grid, 256, 0, st>>>(x, n_in, x_stride, h_dev, len_h, up, down, n_pre_remove, n_out, y_stride, y);
   count_launch();
   return cudaGetLastError();
 }

@@ -435,11 +435,12 @@ __global__ void __launch_bounds__(kThreads, 2)
     // with two power-tile buffers no barrier is needed here: the next tile writes
     // the other buffer and the tile after that is separated by the next tile's
     // __syncthreads; with one buffer the readers must drain first
-    // One power-tile buffer: its readers must be done before the next tile's split step writes
-    // it.  The block barrier every tile already has before that point does the job: the one after
-    // the span loads (single span buffer, early prefetch) or the one after the plain loader's
-    // fill; only the remaining TMA modes need a barrier of their own here.
-    if (p.pt_bufs == 1 && p.use_tma && !(p.span_bufs == 1 && p.early_tma)) __syncthreads();
+    // One power-tile buffer: its readers must be done before the next tile's first split step
+    // writes it.  A block barrier the next tile already has before that point does the job: the
+    // one after the plain loader's fill, or the one after the span loads (single span buffer, early
+    // prefetch) when the whole tile is transformed in one iteration; every other mode needs a
+    // barrier of its own here.
+    if (p.pt_bufs == 1 && p.use_tma && !(p.span_bufs == 1 && p.early_tma && p.TF == FPI)) __syncthreads();
   }
 }
 

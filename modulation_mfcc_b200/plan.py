@@ -371,6 +371,63 @@ class Plan:
         )
         return out
 
+    def pcm16_to_f32(self, pcm16):
+        """int16 PCM (CUDA tensor or numpy) -> float32 in [-1, 1) on the device (x / 32768)."""
+        torch = _torch()
+        x = pcm16 if isinstance(pcm16, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(pcm16))
+        x = x.to(device=torch.device("cuda", self.cfg.device), dtype=torch.int16).contiguous()
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        check(_lib.lib().mmf_pcm16_to_f32(self._h, x.data_ptr(), x.numel(), y.data_ptr(), _stream_ptr(x.device)))
+        return y
+
+    def resample_poly(self, x, up: int, down: int):
+        """``scipy.signal.resample_poly(x, up, down, axis=-1)`` (default Kaiser-5 FIR, constant
+        padding) for float32 rows on the device.  The filter is designed on the host exactly as
+        scipy designs it; the polyphase convolution runs on the GPU."""
+        torch = _torch()
+        import math
+
+        import scipy.signal
+
+        x = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
+        x = x.to(device=torch.device("cuda", self.cfg.device), dtype=torch.float32)
+        squeeze = x.ndim == 1
+        if squeeze:
+            x = x[None, :]
+        x = x.contiguous()
+        g = math.gcd(int(up), int(down))
+        up, down = int(up) // g, int(down) // g
+        n_in = x.shape[-1]
+        if up == 1 and down == 1:
+            return x[0] if squeeze else x
+        n_out = n_in * up
+        n_out = n_out // down + bool(n_out % down)
+        # scipy/signal/_signaltools.py resample_poly: filter design and edge bookkeeping
+        max_rate = max(up, down)
+        half_len = 10 * max_rate
+        h = scipy.signal.firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)).astype(np.float32) * up
+        n_pre_pad = down - half_len % down
+        n_post_pad = 0
+        n_pre_remove = (half_len + n_pre_pad) // down
+
+        from scipy.signal._upfirdn import _output_len
+
+        while _output_len(len(h) + n_pre_pad + n_post_pad, n_in, up, down) < n_out + n_pre_remove:
+            n_post_pad += 1
+        h = np.concatenate((np.zeros(n_pre_pad, dtype=h.dtype), h, np.zeros(n_post_pad, dtype=h.dtype)))
+        h = np.ascontiguousarray(h, dtype=np.float32)
+        y = torch.empty((x.shape[0], n_out), device=x.device, dtype=torch.float32)
+        for c0 in range(0, x.shape[0], 65535):
+            xs = x[c0 : c0 + 65535]
+            ys = y[c0 : c0 + 65535]
+            check(
+                _lib.lib().mmf_resample_poly(
+                    self._h, xs.data_ptr(), xs.shape[0], n_in, xs.stride(0), h.ctypes.data, len(h), up, down,
+                    n_pre_remove, n_out, ys.data_ptr(), ys.stride(0), _stream_ptr(x.device),
+                )
+            )
+        return y[0] if squeeze else y
+
     def mfcc_change(self, pcm, prm: mmf_change_params, *, want_logmel=False, want_mfcc=False, want_delta=False):
         """Whole get_MFCCS_change on device-resident PCM -> dict of CUDA tensors."""
         torch = _torch()
@@ -433,11 +490,13 @@ class Plan:
         totChange/mfcc/delta/modspec/band_energy; ``out`` may hold preallocated
         (ideally pinned) numpy arrays to receive the results."""
         pcm_host = np.asarray(pcm_host)
-        if pcm_host.dtype != np.float32:
+        pcm16 = pcm_host.dtype == np.int16  # raw WAV samples: scaled by 1/32768 on the device
+        if not pcm16 and pcm_host.dtype != np.float32:
             pcm_host = pcm_host.astype(np.float32)
         if pcm_host.ndim == 1:
             pcm_host = pcm_host[None, :]
-        if pcm_host.strides[1] != 4:
+        isz = pcm_host.dtype.itemsize
+        if pcm_host.strides[1] != isz:
             pcm_host = np.ascontiguousarray(pcm_host)
         B, N = pcm_host.shape
         T = self.num_frames(N)
@@ -470,13 +529,14 @@ class Plan:
                 ptr[k] = a.ctypes.data
             else:
                 ptr[k] = None
+        fn = _lib.lib().mmf_features_host_pcm16 if pcm16 else _lib.lib().mmf_features_host
         check(
-            _lib.lib().mmf_features_host(
+            fn(
                 self._h,
                 pcm_host.ctypes.data,
                 B,
                 N,
-                pcm_host.strides[0] // 4 if B > 1 else N,
+                pcm_host.strides[0] // isz if B > 1 else N,
                 C.byref(prm),
                 C.byref(mp) if mp is not None else None,
                 ptr["totChange"],
@@ -491,11 +551,13 @@ class Plan:
     def mfcc_change_host(self, pcm_host: np.ndarray, prm: mmf_change_params, *, want_mfcc: bool = False):
         """Host buffers in and out through the single C-ABI call (H2D/D2H inside)."""
         pcm_host = np.asarray(pcm_host)
-        if pcm_host.dtype != np.float32:
+        pcm16 = pcm_host.dtype == np.int16  # raw WAV samples: scaled by 1/32768 on the device
+        if not pcm16 and pcm_host.dtype != np.float32:
             pcm_host = pcm_host.astype(np.float32)
         if pcm_host.ndim == 1:
             pcm_host = pcm_host[None, :]
-        if pcm_host.strides[1] != 4:
+        isz = pcm_host.dtype.itemsize
+        if pcm_host.strides[1] != isz:
             pcm_host = np.ascontiguousarray(pcm_host)
         B, N = pcm_host.shape
         T = self.num_frames(N)

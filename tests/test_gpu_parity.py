@@ -430,3 +430,55 @@ def test_full_size_properties(cuda_device):
     lhs = 2 * P.double().sum(dim=1) - P[:, 0].double() - P[:, -1].double()
     rhs = 512 * (fr**2).sum(dim=-1)
     assert float(((lhs - rhs).abs() / rhs).max()) < 1e-5
+
+
+def test_pcm16_host_path_is_bit_identical(cuda_device):
+    """int16 PCM in (scaled by 1/32768 on the device) == the float32 call on x/32768."""
+    sr = 16000
+    rng = np.random.default_rng(5)
+    pcm16 = np.clip(np.round(synth_batch(80, 5, sr * 3, sr) * 32768.0), -32768, 32767).astype(np.int16)
+    pcm16[0, :10] = [-32768, 32767, 0, 1, -1, 2, -2, 100, -100, 5]
+    f32 = pcm16.astype(np.float32) / 32768.0
+    fx = mm.FeatureExtractor(sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
+    want = ("totChange", "mfcc", "delta", "modspec", "band_energy")
+    a = {k: v.copy() for k, v in fx.host_call(pcm16, want=want).items()}
+    b = fx.host_call(f32, want=want)
+    for k in want:
+        assert np.array_equal(a[k], b[k]), k
+    ref = oracle.mfcc_features(f32[2], sr)
+    assert np.max(np.abs(a["mfcc"][2] - ref["mfcc"])) < ABS_TOL
+    torch = _torch()
+    y = fx.plan.pcm16_to_f32(torch.as_tensor(pcm16).cuda()).cpu().numpy()
+    assert np.array_equal(y, f32)
+
+
+@pytest.mark.parametrize("up,down,n", [(160, 441, 44100), (1, 2, 10001), (3, 1, 5000), (441, 160, 8000), (2, 3, 97)])
+def test_resample_poly_matches_scipy(up, down, n, cuda_device):
+    rng = np.random.default_rng(up * 1000 + down)
+    x = rng.standard_normal((3, n)).astype(np.float32)
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    y = plan.resample_poly(x, up, down).cpu().numpy()
+    ref = scipy.signal.resample_poly(x.astype(np.float64), up, down, axis=-1)
+    assert y.shape == ref.shape
+    assert np.max(np.abs(y - ref)) < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_load_channel_wav_pcm16_and_resample(cuda_device, tmp_path):
+    """load_channel: WAV parse on the host, PCM16 scaling and rate conversion on the device."""
+    from scipy.io import wavfile
+
+    sr_file, sr = 44100, 16000
+    y = synth_clip(7, sr_file * 2, sr_file)
+    pcm = np.clip(np.round(y * 32767.0), -32768, 32767).astype(np.int16)
+    path = str(tmp_path / "clip.wav")
+    wavfile.write(path, sr_file, pcm)
+    got = mm.load_channel(path, sr)
+    want = scipy.signal.resample_poly(pcm.astype(np.float64) / 32768.0, 160, 441)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert np.max(np.abs(got - want)) < 2e-5
+    same = mm.load_channel(path, sr_file)
+    assert np.array_equal(same, pcm.astype(np.float32) / 32768.0)
+    # a path goes straight through get_MFCCS_change like an array does (script/mfcc.py:372-380)
+    tot_p, T_p = mm.get_MFCCS_change(path, sr, **{**KW_GUI, "tStep": 0.01, "maxFreq": 8000, "minFreq": 0})
+    tot_a, T_a = mm.get_MFCCS_change(got, sr, **{**KW_GUI, "tStep": 0.01, "maxFreq": 8000, "minFreq": 0})
+    assert np.array_equal(T_p, T_a) and np.array_equal(tot_p, tot_a)
