@@ -333,7 +333,7 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        n_cpu = 256
+        n_cpu = CLIPS  # the whole batch of one step: ~20 core-seconds of numpy/scipy work
         vals, times, cores = cpu_throughput(n_cpu, repeats=1, warmup=0)
         cpu = {
             "value": vals[0],
