@@ -94,13 +94,13 @@ def cpu_throughput(n_clips: int, repeats: int = 1, warmup: int = 0):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return None
     cores = os.cpu_count() or 1
-    n_clips = max(64, min(CLIPS, 4 * cores))
+    n_clips = CLIPS  # the full batch of one step (about 20 core-seconds of numpy/scipy work per step)
     vals, times, cores = cpu_throughput(n_clips, repeats=args.steps, warmup=args.warmup)
     total = sum(times)
     value = n_clips * SECONDS * len(times) / total
-    sample = f"{n_clips} of the {CLIPS} clips per step (oracle.mfcc_features per clip, fork pool over all cores, BLAS threads = 1)"
+    sample = f"all {n_clips} clips of the workload per step (oracle.mfcc_features per clip, fork pool over all cores, BLAS threads = 1)"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -115,13 +115,12 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_step": n_clips, "note": "CPU arm: bounded sample of the workload per step"},
+        "config": {"workload": WORKLOAD, "clips_per_step": n_clips, "note": "CPU arm: the numpy/scipy restatement of the reference path (the reference itself cannot be installed offline: DESIGN.md section 2)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-    return 0
+    return line
 
 
 # --------------------------------------------------------------------------- clocks
@@ -211,7 +210,11 @@ def run_b200(args):
     pcm = mm.synth_batch_device(CLIPS, N_SAMPLES, SR, seed=1234 + rank, device=dev)
     T = plan.num_frames(N_SAMPLES)
     Lw, Hw, nfft, bins = fx.modspec_geometry(T)
-    gathered = torch.empty((world * CLIPS, T), device=dev, dtype=torch.float64) if world > 1 else None
+    # the only collective: final gather of the per-clip feature.  It is issued asynchronously (NCCL's
+    # own stream, ordered after the step's kernels) into one of two buffers, so it overlaps the next
+    # step's compute; every gather is waited for inside the timed region.
+    gathered = [torch.empty((world * CLIPS, T), device=dev, dtype=torch.float64) for _ in range(2)] if world > 1 else None
+    pending = []
 
     k1_events = []
 
@@ -225,12 +228,25 @@ def run_b200(args):
             k1_events.append((e0, e1))
         res = plan.change_from_logmel(lm, cmax, prm, clamp_in_place=False)  # clamp+DCT+delta, IIR, derivative+norm, IIR
         mag, band = plan.modspec(res["mfcc"], Lw, Hw, nfft, bins)
-        if world > 1:  # the only collective: final gather of the per-clip feature
-            dist.all_gather_into_tensor(gathered, res["totChange"])
+        if world > 1:
+            if len(pending) >= 2:  # the buffer about to be reused must have been filled
+                w, keep = pending.pop(0)
+                w.wait()
+            buf = gathered[step.count % 2]
+            step.count += 1
+            pending.append((dist.all_gather_into_tensor(buf, res["totChange"], async_op=True), res["totChange"]))
         return res, mag, band
+
+    step.count = 0
+
+    def drain():
+        while pending:
+            w, keep = pending.pop(0)
+            w.wait()
 
     for _ in range(max(args.warmup, 3)):
         step(False)
+    drain()
     torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local)
@@ -241,6 +257,7 @@ def run_b200(args):
     ev0.record()
     for _ in range(args.steps):
         step(True)
+    drain()  # every gather has landed before the clock stops
     ev1.record()
     torch.cuda.synchronize()
     barrier()
@@ -310,7 +327,7 @@ def run_b200(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return 0
+        return None
 
     peaks = {}
     try:
@@ -361,7 +378,7 @@ def run_b200(args):
             "clips_per_gpu": CLIPS,
             "frames_per_clip": T,
             "l2": "inputs are 655 MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
-            "collective": "all_gather_into_tensor of totChange per step" if world > 1 else "none",
+            "collective": "all_gather_into_tensor of totChange per step, asynchronous, overlapping the next step" if world > 1 else "none",
             "fp64_stages": "zero-phase Butterworth, derivative/norm and the trajectory FFT run in f64",
         },
         "clocks": clocks,
@@ -397,10 +414,26 @@ def run_b200(args):
         },
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line
+
+
+class _StdoutToStderr:
+    """Everything written to fd 1 while the bench runs (NCCL's version banner, library chatter)
+    goes to stderr, so that stdout carries exactly one line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -411,9 +444,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    with _StdoutToStderr():
+        line = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":
