@@ -256,33 +256,50 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   }
   host_dct(cfg->n_mfcc, cfg->n_mels, dct);
 
-  // ---- tensor-core mel tables: the (n-tile of 8 bands, k-tile of 8 bins) blocks of the filterbank
-  // that are not all zero, n-major; per block the B fragments of mma.m16n8k8
-  // (b0: k = lane%4, b1: k = lane%4 + 4; n = lane/4) as plain fp32 (split into TF32 hi/lo on the fly)
-  const int NT = (cfg->n_mels + 7) / 8;
+  // ---- tensor-core mel tables.  An n-tile is a run of up to 8 consecutive bands (the N of
+  // mma.m16n8k8); it is cut short when its bands span more than kTileBlocks k-tiles of 8 bins, so
+  // that the wide top bands do not pile all their blocks on one warp.  Per tile: the k-tiles whose
+  // 8x8 block of the filterbank is not all zero, and per block the B fragments
+  // (b0: k = lane%4, b1: k = lane%4 + 4; n = lane/4) as plain fp32 (split into TF32 hi/lo on the fly).
   std::vector<float2> mma_bw;
-  std::vector<int> mma_pk8, mma_npair(NT + 1, 0);
+  std::vector<int> mma_pk8, mma_npair(1, 0), mma_tile;  // mma_tile[j] = first band | bands << 16
   {
-    const int F = p->F;
+    const int F = p->F, kTileBlocks = 8;
     auto wgt = [&](int k, int band) -> float {
       return (k < F && band < cfg->n_mels) ? mel[(size_t)band * F + k] : 0.0f;
     };
-    for (int n = 0; n < NT; ++n) {
-      mma_npair[n] = (int)mma_pk8.size();
+    auto blocks_of = [&](int b0, int nb, std::vector<int>* out) {
+      int cnt = 0;
       for (int k8 = 0; k8 < (F + 7) / 8; ++k8) {
         bool any = false;
         for (int k = 8 * k8; k < 8 * k8 + 8 && !any; ++k)
-          for (int b = 8 * n; b < 8 * n + 8 && !any; ++b) any = wgt(k, b) != 0.0f;
-        if (!any) continue;
+          for (int b = b0; b < b0 + nb && !any; ++b) any = wgt(k, b) != 0.0f;
+        if (any) {
+          ++cnt;
+          if (out) out->push_back(k8);
+        }
+      }
+      return cnt;
+    };
+    for (int b0 = 0; b0 < cfg->n_mels;) {
+      int nb = 1;
+      while (nb < 8 && b0 + nb < cfg->n_mels && blocks_of(b0, nb + 1, nullptr) <= kTileBlocks) ++nb;
+      std::vector<int> ks;
+      blocks_of(b0, nb, &ks);
+      for (int k8 : ks) {
         mma_pk8.push_back(k8);
         for (int lane = 0; lane < 32; ++lane) {
           const int g = lane >> 2, t4 = lane & 3;
-          mma_bw.push_back(make_float2(wgt(8 * k8 + t4, 8 * n + g), wgt(8 * k8 + t4 + 4, 8 * n + g)));
+          const bool own = g < nb;  // columns beyond the tile's bands belong to the next tile
+          mma_bw.push_back(make_float2(own ? wgt(8 * k8 + t4, b0 + g) : 0.0f, own ? wgt(8 * k8 + t4 + 4, b0 + g) : 0.0f));
         }
       }
+      mma_tile.push_back(b0 | (nb << 16));
+      mma_npair.push_back((int)mma_pk8.size());
+      b0 += nb;
     }
-    mma_npair[NT] = (int)mma_pk8.size();
   }
+  const int NT = (int)mma_tile.size();
   p->mma_n_pairs = (int)mma_pk8.size();
 
   // ---- tile geometry.  Preference: the widest tile first (32 frames = one frame per lane /
@@ -317,7 +334,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     const int span = (tf - 1) * cfg->hop_length + cfg->n_fft + p->lead + 3;
     const int alloc = (span + 255) / 256 * 256;
     return stft_smem_bytes(cfg->n_fft, alloc, span_bufs, pitch_for(tf), pt_bufs, p->packed,
-                           stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, mel_mma, p->mma_n_pairs));
+                           stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, mel_mma, p->mma_n_pairs, NT));
   };
   auto choose = [&](int mel_mma) {
     Geo g;
@@ -345,7 +362,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   // FP32 walk: the filterbank is 95-98 % zeros and the split-precision MMA path measured 3-7 %
   // slower on every BASELINE shape.
   Geo gs = choose(0), gm = choose(1);
-  const bool units_fit = NT * 2 <= 8 * 16;
+  const bool units_fit = NT * 2 <= 8 * 16 && NT <= 255;
   p->mel_mma = ((cfg->flags & MMF_FLAG_MMA_MEL) && units_fit && gm.tf != 0 && gm.tf >= gs.tf &&
                 gm.ctas >= gs.ctas)
                    ? 1
@@ -372,7 +389,8 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   p->ctas_per_sm = g.ctas;
   p->ppitch = pitch_for(tf);
   p->smem = g.smem;
-  p->mel_tab_bytes = stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, p->mel_mma, p->mma_n_pairs);
+  p->mel_tab_bytes = stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, p->mel_mma, p->mma_n_pairs, NT);
+  p->mma_n_tiles = NT;
 
   // ---- tensor-core mel work list: unit = (n-tile, 16-frame m-tile), cost = blocks of the n-tile;
   // longest-processing-time assignment to the 8 warps (each unit is produced by exactly one warp)
@@ -446,6 +464,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
       (e = upload(&p->d_band_split, band_split)) != cudaSuccess ||
       (e = upload(&p->d_mma_bw, mma_bw)) != cudaSuccess || (e = upload(&p->d_mma_pk8, mma_pk8)) != cudaSuccess ||
       (e = upload(&p->d_mma_npair, mma_npair)) != cudaSuccess ||
+      (e = upload(&p->d_mma_tile, mma_tile)) != cudaSuccess ||
       (e = upload(&p->d_mma_units, mma_units)) != cudaSuccess ||
       (e = upload(&p->d_w2, w2)) != cudaSuccess || (e = upload(&p->d_dct, dct_pad)) != cudaSuccess) {
     mmf_plan_destroy(p);
@@ -475,6 +494,7 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_mma_bw);
   cudaFree(p->d_mma_pk8);
   cudaFree(p->d_mma_npair);
+  cudaFree(p->d_mma_tile);
   cudaFree(p->d_mma_units);
   cudaFree(p->d_w2);
   cudaFree(p->d_dct);
@@ -534,6 +554,8 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   a.mma_bw = p->d_mma_bw;
   a.mma_pk8 = p->d_mma_pk8;
   a.mma_npair = p->d_mma_npair;
+  a.mma_tile = p->d_mma_tile;
+  a.mma_n_tiles = p->mma_n_tiles;
   a.mma_units = p->d_mma_units;
   if (const char* e = std::getenv("MMF_DEBUG_SKIP")) a.debug_skip = std::atoi(e);
   a.early_tma = 1;

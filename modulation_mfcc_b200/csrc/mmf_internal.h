@@ -38,7 +38,9 @@ struct StftArgs {
   int mel_tab_bytes;     // shared-memory bytes of the mel tables of the active mode
   const float2* mma_bw;  // [n_pairs][32] B fragments: W[8*k8 + lane%4 (+4)][8*n + lane/4], n-major
   const int* mma_pk8;    // [n_pairs] k-tile of each block
-  const int* mma_npair;  // [NT + 1] block range of each 8-band n-tile
+  const int* mma_npair;  // [NT + 1] block range of each n-tile
+  const int* mma_tile;   // [NT] first band | bands << 16 of each n-tile (up to 8 consecutive bands)
+  int mma_n_tiles;
   const int* mma_units;  // [8][16] (n | m << 8) units of each warp, -1 terminated
   int early_tma;         // single span buffer: prefetch the next tile right after the load phase (extra barrier)
   int debug_skip;        // profiling aid (MMF_DEBUG_SKIP): bit 0 skips the FFT phase, bit 1 the mel phase
@@ -63,7 +65,7 @@ struct StftGeometry {
 
 bool stft_packed_supported(int n_fft);
 int stft_geometry(int n_fft, int packed, StftGeometry* g);
-size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs);
+size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int n_tiles);
 size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed,
                        size_t mel_tab_bytes);
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
@@ -167,6 +169,8 @@ struct mmf_plan {
   float2* d_mma_bw = nullptr;
   int* d_mma_pk8 = nullptr;
   int* d_mma_npair = nullptr;
+  int* d_mma_tile = nullptr;
+  int mma_n_tiles = 0;
   int* d_mma_units = nullptr;
   int mma_n_pairs = 0;
   size_t mel_tab_bytes = 0;

@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   // mel tables: sparse FP32 walk            | tensor cores
   //   s_w2  [F] (falling, rising) weights   |   s_bw    [n_pairs][32] B fragments (fp32, split on the fly)
   //   s_seg [n_mels + 2] segment starts     |   s_pk8   [n_pairs] k-tile of each pair
-  //   s_mb  [kMaxWorkers + 2] band groups   |   s_npair [NT + 1] pair range of each 8-band n-tile
+  //   s_mb  [kMaxWorkers + 2] band groups   |   s_npair [NT + 1] pair range of each n-tile
+  //                                         |   s_tile  [NT] first band | bands << 16 of each n-tile
   //                                         |   s_units [8][kMaxUnits] (n | m << 8) work list per warp
   float2* s_w2 = s_win + C::M;
   int* s_seg = reinterpret_cast<int*>(s_w2 + C::F);
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   float2* s_bw = s_win + C::M;
   int* s_pk8 = reinterpret_cast<int*>(s_bw + (size_t)p.mma_n_pairs * 32);
   int* s_npair = s_pk8 + p.mma_n_pairs;
-  int* s_units = s_npair + ((p.n_mels + 7) / 8 + 1);
+  int* s_tile = s_npair + (p.mma_n_tiles + 1);
+  int* s_units = s_tile + p.mma_n_tiles;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(
       reinterpret_cast<unsigned char*>(s_win + C::M) + ((p.mel_tab_bytes + 15) & ~15));  // [2]
 
@@ -165,7 +167,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   for (int i = tid; i < C::TW1; i += kThreads) s_tw1[i] = make_tw<V>(p.tw1[i]);
   for (int i = tid; i < C::TW2; i += kThreads) s_tw2[i] = make_tw<V>(p.tw2[i]);
   if (p.mel_mma) {
-    const int NT = (p.n_mels + 7) / 8;
+    const int NT = p.mma_n_tiles;
+    for (int i = tid; i < NT; i += kThreads) s_tile[i] = p.mma_tile[i];
     for (int i = tid; i < p.mma_n_pairs * 32; i += kThreads) s_bw[i] = p.mma_bw[i];
     for (int i = tid; i < p.mma_n_pairs; i += kThreads) s_pk8[i] = p.mma_pk8[i];
     for (int i = tid; i < NT + 1; i += kThreads) s_npair[i] = p.mma_npair[i];
@@ -388,12 +391,13 @@ __global__ void __launch_bounds__(kThreads, 2)
           mma_tf32(acc_lh, al, bh0, bh1);
         }
         // acc: (frame g, band 2*t4), (g, 2*t4+1), (g+8, 2*t4), (g+8, 2*t4+1) of this unit
-        const int band0 = 8 * n + 2 * t4;
+        const int tile = s_tile[n];
+        const int band0 = (tile & 0xffff) + 2 * t4, nb = tile >> 16;
         float* orow = p.logmel + ((size_t)clip * p.n_mels + band0) * p.T + t0 + 16 * m + g;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int f = 16 * m + g + ((e & 2) ? 8 : 0);
-          if (f < t_valid && band0 + (e & 1) < p.n_mels) {
+          if (f < t_valid && 2 * t4 + (e & 1) < nb) {
             // 10*log10(x) = 10*log10(2) * log2(x); lg2.approx is within 1e-6 dB here (x >= amin, never denormal)
             const float val = acc[e] + (acc_hl[e] + acc_lh[e]);
             const float db = 3.01029995663981195f * fast_log2(fmaxf(p.amin, val));
@@ -448,10 +452,10 @@ __global__ void __launch_bounds__(kThreads, 2)
 // host side
 // ---------------------------------------------------------------------------
 
-size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs) {
+size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int n_tiles) {
   const int F = n_fft / 2 + 1;
   if (mel_mma)
-    return (size_t)n_pairs * 32 * 8 + (size_t)n_pairs * 4 + (size_t)((n_mels + 7) / 8 + 1) * 4 + 8 * kMaxUnits * 4;
+    return (size_t)n_pairs * 32 * 8 + (size_t)n_pairs * 4 + (size_t)(2 * n_tiles + 1) * 4 + 8 * kMaxUnits * 4;
   return (size_t)F * 8 + (size_t)((n_mels + 2 + 1) & ~1) * 4 + (size_t)(kMaxWorkers + 2) * 4;
 }
 
