@@ -80,10 +80,8 @@ constexpr int kMaxWorkers = 256;  // mel band groups per CTA: 8 warps * (32 / TF
 // One thread queues the TMA boxes of a tile's PCM span.  Negative and
 // past-the-end sample coordinates are zero-filled by the TMA unit.
 template <int NFFT>
-__device__ __forceinline__ void issue_span(const CUtensorMap* tmap, const StftArgs& p, long tile, float* dst,
+__device__ __forceinline__ void issue_span(const CUtensorMap* tmap, const StftArgs& p, int clip, int t0, float* dst,
                                            uint64_t* bar) {
-  const int clip = (int)(tile / p.tiles_per_clip);
-  const int t0 = (int)(tile % p.tiles_per_clip) * p.TF;
   // TMA box start addresses must be 16-byte aligned: round the first sample down
   // to a multiple of 4 floats; the kernel adds the remainder to its frame offsets
   const int g0 = (t0 * p.hop - NFFT / 2 - p.lead) & ~3;
@@ -214,13 +212,29 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int lead = p.lead;  // samples loaded ahead of the first frame (pre-emphasis history)
   const long n_tiles = p.n_tiles;
 
+  // tile -> (clip, tile within clip), advanced by gridDim.x per iteration without dividing again
   long tile = blockIdx.x;
-  if (p.use_tma && tid == 0 && tile < n_tiles) issue_span<NFFT>(&tmap, p, tile, s_span, &s_bar[0]);
+  const int tpc = p.tiles_per_clip;
+  const int step_q = (int)(gridDim.x / (unsigned)tpc), step_r = (int)(gridDim.x % (unsigned)tpc);
+  int clip = (int)(tile / tpc), tin = (int)(tile % tpc);
+  auto next_tile = [&](int& c, int& t) {
+    c += step_q;
+    t += step_r;
+    if (t >= tpc) {
+      t -= tpc;
+      ++c;
+    }
+  };
+  // TF is a power of two
+  int tf_shift = 0;
+  while ((1 << tf_shift) < p.TF) ++tf_shift;
+  if (p.use_tma && tid == 0 && tile < n_tiles) issue_span<NFFT>(&tmap, p, clip, tin << tf_shift, s_span, &s_bar[0]);
 
-  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it, next_tile(clip, tin)) {
     const int b = p.span_bufs == 2 ? (it & 1) : 0;
-    const int clip = (int)(tile / p.tiles_per_clip);
-    const int t0 = (int)(tile % p.tiles_per_clip) * p.TF;
+    const int t0 = tin << tf_shift;
+    int nclip = clip, ntin = tin;  // the tile after this one (prefetch target)
+    next_tile(nclip, ntin);
     float* span = s_span + (size_t)b * p.span_alloc;
     // the span starts at the 16-byte aligned sample at or below the first needed one
     const int g_first = t0 * p.hop - NFFT / 2 - lead;
@@ -232,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       // finished before the __syncthreads that closed the previous tile's FFT phase);
       // one span buffer: the prefetch is issued after this tile's FFT phase instead
       if (p.span_bufs == 2 && tid == 0 && tile + gridDim.x < n_tiles)
-        issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span + (size_t)(b ^ 1) * p.span_alloc, &s_bar[b ^ 1]);
+        issue_span<NFFT>(&tmap, p, nclip, ntin << tf_shift, s_span + (size_t)(b ^ 1) * p.span_alloc, &s_bar[b ^ 1]);
       mbar_wait(&s_bar[b], (uint32_t)(p.span_bufs == 2 ? (it >> 1) : it) & 1u);
     } else {
       // plain coalesced loader (clip stride or base not 16-byte aligned)
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         // every frame of the tile now sits in registers: the single span buffer is free, so the
         // next tile's PCM streams in underneath this tile's transform and mel projection
         __syncthreads();
-        if (tid == 0 && tile + gridDim.x < n_tiles) issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span, &s_bar[0]);
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue_span<NFFT>(&tmap, p, nclip, ntin << tf_shift, s_span, &s_bar[0]);
       }
       ph_pass1<NFFT>(v, s_tw1, tau);
       if constexpr (TR::kXParts == 1) {
@@ -343,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     __syncthreads();  // power tile complete
     if (p.use_tma && p.span_bufs == 1 && (!p.early_tma || (p.debug_skip & 1)) && tid == 0 && tile + gridDim.x < n_tiles)
-      issue_span<NFFT>(&tmap, p, tile + gridDim.x, s_span, &s_bar[0]);  // (profiling mode without FFT phase)
+      issue_span<NFFT>(&tmap, p, nclip, ntin << tf_shift, s_span, &s_bar[0]);  // (profiling mode without FFT phase)
 
     const int t_valid = min(p.TF, p.T - t0);
     if (p.power != nullptr) {
@@ -412,8 +426,8 @@ __global__ void __launch_bounds__(kThreads, 2)
     } else if (p.logmel != nullptr && !(p.debug_skip & 2)) {
       // ---------------- mel phase: lane -> frame, worker (warp or part of one) -> band group.
       // Band groups are balanced on the host by bins + bands (c_api.cu: band_split).
-      const int t = lane % p.TF;
-      const int worker = (tid >> 5) * (32 / p.TF) + lane / p.TF;
+      const int t = lane & (p.TF - 1);
+      const int worker = (tid >> 5) * (32 >> tf_shift) + (lane >> tf_shift);
       const int m0 = s_mb[worker], m1 = s_mb[worker + 1];
       float mx = -FLT_MAX;
       if (m0 < m1 && t < t_valid) {
