@@ -196,6 +196,14 @@ int mmf_features_host_pcm16(mmf_plan* plan, const int16_t* pcm16_host, int64_t n
                             double* tot_host, float* mfcc_host, float* delta_host, float* mag_host,
                             float* band_host);
 
+/* Local extrema of each float64 row with scipy.signal.find_peaks' default semantics (strictly higher
+ * than both neighbours; a flat top reports its middle sample; end samples never qualify) -- the
+ * landmark step the GUI runs on the curve (script/main.py:1566, :1601; script/calc.py:669, :681).
+ * idx_dev [rows, max_peaks] receives the indices in ascending order, count_dev [rows] the number
+ * found (may exceed max_peaks: only the first max_peaks are stored).  minima != 0: peaks of -x. */
+int mmf_find_peaks(mmf_plan* plan, const double* x_dev, int64_t rows, int64_t T, int64_t row_stride, int32_t minima,
+                   int32_t max_peaks, int32_t* idx_dev, int32_t* count_dev, void* stream);
+
 /* Device-side PCM16 -> float32 in [-1, 1): y = x / 32768 (script/mfcc.py:373, :284 decode step). */
 int mmf_pcm16_to_f32(mmf_plan* plan, const int16_t* pcm16_dev, int64_t n, float* pcm_dev, void* stream);
 

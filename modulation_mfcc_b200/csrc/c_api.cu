@@ -1021,6 +1021,17 @@ int mmf_features_host_pcm16(mmf_plan* plan, const int16_t* pcm16_host, int64_t n
                             delta_host, mag_host, band_host);
 }
 
+int mmf_find_peaks(mmf_plan* plan, const double* x_dev, int64_t rows, int64_t T, int64_t row_stride, int32_t minima,
+                   int32_t max_peaks, int32_t* idx_dev, int32_t* count_dev, void* stream) {
+  if (!plan || !x_dev || !idx_dev || !count_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (rows < 1 || T < 1 || max_peaks < 1 || rows > (1L << 26)) return fail(MMF_ERR_INVALID, "bad sizes");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  cudaError_t e = find_peaks_launch(x_dev, rows, T, row_stride, minima, max_peaks, idx_dev, count_dev,
+                                    (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "find_peaks_kernel launch");
+  return MMF_OK;
+}
+
 int mmf_pcm16_to_f32(mmf_plan* plan, const int16_t* pcm16_dev, int64_t n, float* pcm_dev, void* stream) {
   if (!plan || !pcm16_dev || !pcm_dev) return fail(MMF_ERR_INVALID, "NULL argument");
   if (n < 1) return fail(MMF_ERR_INVALID, "n must be positive");

@@ -115,6 +115,8 @@ cudaError_t modspec_fast_launch(const float* mfcc, long n_clips, int n_coef, lon
 cudaError_t rms_launch(const float* pcm, long n_clips, long n, long stride, int frame_length, int hop, int pad,
                        long T, float* out, cudaStream_t st);
 cudaError_t fill_i32_launch(int* p, long n, int v, cudaStream_t st);
+cudaError_t find_peaks_launch(const double* x, long rows, long T, long stride, int minima, int max_peaks, int* idx,
+                              int* count, cudaStream_t st);
 cudaError_t pcm16_to_f32_launch(const int16_t* x, long n, float* y, cudaStream_t st);
 cudaError_t resample_poly_launch(const float* x, long n_clips, long n_in, long x_stride, const float* h_dev, int len_h,
                                  int up, int down, long n_pre_remove, long n_out, long y_stride, float* y,

@@ -669,6 +669,56 @@ cudaError_t resample_poly_launch(const float* x, long n_clips, long n_in, long x
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Local maxima of each row with scipy.signal.find_peaks' default semantics (the step after the
+// path: script/main.py:1566, :1601 and script/calc.py:669, :681 call find_peaks(+-curve)):
+// a peak is a sample, or a flat run of equal samples, strictly higher than both neighbours;
+// a flat run reports its middle index (left + right) / 2; the first and last sample never are.
+// One warp per row; peaks come out in ascending order (ballot + prefix popcount).  `sign` = -1
+// finds minima.  count[row] holds the total number found even when it exceeds max_peaks.
+// ---------------------------------------------------------------------------
+__global__ void find_peaks_kernel(const double* __restrict__ x, long rows, long T, long stride, double sign,
+                                  int max_peaks, int* __restrict__ idx, int* __restrict__ count) {
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const double* xr = x + row * stride;
+  int* out = idx + row * (long)max_peaks;
+  int base = 0;
+  for (long t0 = 1; t0 < T - 1; t0 += 32) {
+    const long t = t0 + lane;
+    bool is_peak = false;
+    int where = 0;
+    if (t < T - 1) {
+      const double v = sign * xr[t];
+      if (sign * xr[t - 1] < v) {  // rising edge: the run starting here may be a peak
+        long r = t;
+        while (r + 1 < T && sign * xr[r + 1] == v) ++r;
+        if (r + 1 < T && sign * xr[r + 1] < v) {
+          is_peak = true;
+          where = (int)((t + r) / 2);
+        }
+      }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, is_peak);
+    if (is_peak) {
+      const int pos = base + __popc(mask & ((1u << lane) - 1u));
+      if (pos < max_peaks) out[pos] = where;
+    }
+    base += __popc(mask);
+  }
+  if (lane == 0) count[row] = base;
+}
+
+cudaError_t find_peaks_launch(const double* x, long rows, long T, long stride, int minima, int max_peaks, int* idx,
+                              int* count, cudaStream_t st) {
+  const long threads = rows * 32;
+  find_peaks_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, rows, T, stride, minima ? -1.0 : 1.0, max_peaks,
+                                                                     idx, count);
+  count_launch();
+  return cudaGetLastError();
+}
+
 __global__ void fill_i32_kernel(int* p, long n, int v) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

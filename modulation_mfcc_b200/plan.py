@@ -371,6 +371,29 @@ class Plan:
         )
         return out
 
+    def find_peaks(self, x, *, minima: bool = False, max_peaks: int | None = None):
+        """``scipy.signal.find_peaks(x)`` (default arguments) for every float64 row of ``x`` on the
+        device.  Returns ``(idx [rows, max_peaks] int32, count [rows] int32)``; row ``r`` holds its
+        ``min(count[r], max_peaks)`` peak indices in ascending order."""
+        torch = _torch()
+        x = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64))
+        x = x.to(device=torch.device("cuda", self.cfg.device), dtype=torch.float64)
+        if x.ndim == 1:
+            x = x[None, :]
+        x = x.contiguous()
+        rows, T = x.shape
+        if max_peaks is None:
+            max_peaks = max(1, (T - 1) // 2)  # peaks need a lower sample between them
+        idx = torch.full((rows, max_peaks), -1, device=x.device, dtype=torch.int32)
+        cnt = torch.empty((rows,), device=x.device, dtype=torch.int32)
+        check(
+            _lib.lib().mmf_find_peaks(
+                self._h, x.data_ptr(), rows, T, x.stride(0), 1 if minima else 0, max_peaks, idx.data_ptr(), cnt.data_ptr(),
+                _stream_ptr(x.device),
+            )
+        )
+        return idx, cnt
+
     def pcm16_to_f32(self, pcm16):
         """int16 PCM (CUDA tensor or numpy) -> float32 in [-1, 1) on the device (x / 32768)."""
         torch = _torch()

@@ -482,3 +482,29 @@ def test_load_channel_wav_pcm16_and_resample(cuda_device, tmp_path):
     tot_p, T_p = mm.get_MFCCS_change(path, sr, **{**KW_GUI, "tStep": 0.01, "maxFreq": 8000, "minFreq": 0})
     tot_a, T_a = mm.get_MFCCS_change(got, sr, **{**KW_GUI, "tStep": 0.01, "maxFreq": 8000, "minFreq": 0})
     assert np.array_equal(T_p, T_a) and np.array_equal(tot_p, tot_a)
+
+
+def test_find_peaks_matches_scipy(cuda_device):
+    """Landmarks of the curve (script/main.py:1566, :1601): default scipy.signal.find_peaks."""
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((6, 777)).cumsum(axis=-1)
+    x[1] = np.round(x[1])            # flat tops and flat valleys
+    x[2, 100:140] = x[2, 100]        # a long plateau
+    x[3] = 0.0                       # constant row: no peaks
+    x[4, :] = np.arange(777)         # monotone: no peaks
+    sr = 16000
+    y = synth_batch(90, 2, sr * 10, sr)
+    tot, _ = mm.get_MFCCS_change_batch(y, sr, tStep=0.01, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=0, maxFreq=8000,
+                                       outFiltCutOff=[12], n_mels=40)
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    for data in (x, tot):
+        for minima in (False, True):
+            idx, cnt = plan.find_peaks(data, minima=minima)
+            idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+            for r in range(data.shape[0]):
+                ref, _ = scipy.signal.find_peaks(-data[r] if minima else data[r])
+                assert cnt[r] == len(ref)
+                assert np.array_equal(idx[r, : cnt[r]], ref)
+    idx, cnt = plan.find_peaks(x[0], max_peaks=3)
+    ref, _ = scipy.signal.find_peaks(x[0])
+    assert int(cnt[0]) == len(ref) and np.array_equal(idx[0].cpu().numpy(), ref[:3])
