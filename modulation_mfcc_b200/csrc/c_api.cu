@@ -241,7 +241,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   p->F = cfg->n_fft / 2 + 1;
   p->sm_count = prop.multiProcessorCount;
   p->packed = (stft_packed_supported(cfg->n_fft) && !(cfg->flags & MMF_FLAG_SCALAR_FFT)) ? 1 : 0;
-  stft_geometry(cfg->n_fft, p->packed, &p->geo);
+  stft_geometry(cfg->n_fft, p->packed, 256, &p->geo);
   p->lead = cfg->preemph != 0.0f ? 2 : 0;
 
   // ---- constant tables
@@ -305,7 +305,6 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   // ---- tile geometry.  Preference: the widest tile first (32 frames = one frame per lane /
   // two MMA row tiles in the mel phase), then as much double buffering as two CTAs per SM allow
   // (<= 113 KB each: 227 KB per SM, 1 KB reserved per CTA); one CTA per SM as the last resort.
-  const int fpi = p->geo.fpi;
   const int fpw = p->geo.tpf < 32 ? 32 / p->geo.tpf : 1;  // frames per warp in the FFT phase
   auto pitch_for = [&](int tf) {
     if (p->packed) {
@@ -327,34 +326,49 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   const size_t budget2 = 113 * 1024, budget1 = 226 * 1024;
   static const int kBufChoices[4][2] = {{2, 2}, {1, 2}, {2, 1}, {1, 1}};  // {span_bufs, pt_bufs}
   struct Geo {
-    int tf = 0, span_bufs = 2, pt_bufs = 2, ctas = 2;
+    int tf = 0, span_bufs = 2, pt_bufs = 2, ctas = 2, threads = 256;
     size_t smem = 0;
   };
-  auto smem_for = [&](int tf, int span_bufs, int pt_bufs, int mel_mma) {
+  auto smem_for = [&](int tf, int span_bufs, int pt_bufs, int mel_mma, int threads) {
     const int span = (tf - 1) * cfg->hop_length + cfg->n_fft + p->lead + 3;
     const int alloc = (span + 255) / 256 * 256;
     return stft_smem_bytes(cfg->n_fft, alloc, span_bufs, pitch_for(tf), pt_bufs, p->packed,
-                           stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, mel_mma, p->mma_n_pairs, NT));
+                           stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, mel_mma, p->mma_n_pairs, NT), threads);
   };
-  auto choose = [&](int mel_mma) {
-    Geo g;
-    for (int pass = 0; pass < 2 && g.tf == 0; ++pass) {
-      const size_t budget = pass == 0 ? budget2 : budget1;
-      g.ctas = pass == 0 ? 2 : 1;
-      for (int cand = 32; cand >= 1 && g.tf == 0; cand >>= 1) {
-        if (cand < fpi || cand % fpi) continue;
-        for (const auto& ch : kBufChoices) {
-          const size_t b = smem_for(cand, ch[0], ch[1], mel_mma);
-          if (b <= budget) {
-            g.tf = cand;
-            g.span_bufs = ch[0];
-            g.pt_bufs = ch[1];
-            g.smem = b;
-            break;
-          }
+  auto fpi_for = [&](int threads) { return (threads / p->geo.tpf) * (p->packed ? 2 : 1); };
+  // widest tile (then most double buffering) that fits `budget` with CTAs of `threads`
+  auto fit = [&](int mel_mma, int threads, size_t budget, Geo* g) {
+    const int fpi = fpi_for(threads);
+    if (fpi < 1 || fpi > 32) return false;
+    for (int cand = 32; cand >= 1; cand >>= 1) {
+      if (cand < fpi || cand % fpi) continue;
+      for (const auto& ch : kBufChoices) {
+        const size_t b = smem_for(cand, ch[0], ch[1], mel_mma, threads);
+        if (b <= budget) {
+          g->tf = cand;
+          g->span_bufs = ch[0];
+          g->pt_bufs = ch[1];
+          g->smem = b;
+          g->threads = threads;
+          return true;
         }
       }
     }
+    return false;
+  };
+  auto choose = [&](int mel_mma) {
+    Geo g;
+    g.ctas = 2;
+    if (fit(mel_mma, 256, budget2, &g)) return g;
+    g.ctas = 1;
+    // one CTA per SM: 512 threads (16 warps) when the transform groups are whole warps and the
+    // tiles still fit, else 256
+    Geo g512;
+    g512.ctas = 1;
+    const bool ok512 = cfg->n_fft >= 1024 && !mel_mma && fit(mel_mma, 512, budget1, &g512);
+    const bool ok256 = fit(mel_mma, 256, budget1, &g);
+    if (ok512 && (!ok256 || g512.tf >= g.tf) && !std::getenv("MMF_NO_512")) return g512;
+    if (!ok256) g.tf = 0;
     return g;
   };
   // The tensor-core mel (MMF_FLAG_MMA_MEL) keeps its B fragments in shared memory: honoured unless
@@ -371,17 +385,21 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   // debugging / tuning overrides
   if (const char* e = std::getenv("MMF_TF")) {
     const int v = std::atoi(e);
+    const int fpi = fpi_for(256);
+    g.threads = 256;
     if (v >= fpi && v <= 32 && (v & (v - 1)) == 0 && v % fpi == 0) g.tf = v;
     if (const char* e2 = std::getenv("MMF_SPAN_BUFS")) g.span_bufs = std::atoi(e2) == 1 ? 1 : 2;
     if (const char* e3 = std::getenv("MMF_PT_BUFS")) g.pt_bufs = std::atoi(e3) == 1 ? 1 : 2;
-    g.smem = smem_for(g.tf, g.span_bufs, g.pt_bufs, p->mel_mma);
+    g.smem = smem_for(g.tf, g.span_bufs, g.pt_bufs, p->mel_mma, 256);
     g.ctas = g.smem <= budget2 ? 2 : 1;
     if (g.smem > budget1) g.tf = 0;
   }
-  if (g.tf == 0 || fpi > 32) {
+  if (g.tf == 0) {
     delete p;
     return fail(MMF_ERR_UNSUPPORTED, "hop_length/n_fft combination needs more shared memory than one SM has");
   }
+  p->threads = g.threads;
+  stft_geometry(cfg->n_fft, p->packed, p->threads, &p->geo);
   const int tf = g.tf;
   p->TF = tf;
   p->pt_bufs = g.pt_bufs;
@@ -422,7 +440,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   // fill under a binary-searched bound)
   std::vector<int> band_split(257, cfg->n_mels);
   {
-    const int workers = std::min(256, 8 * (32 / tf));
+    const int workers = std::min(256, (p->threads / 32) * (32 / tf));
     const int cbin = 7, cband = 48;  // measured: 7 instructions per bin, 29 per segment + 19 per band
     auto group_cost = [&](int a, int b) {  // bands [a, b): segments a..b
       return cbin * (sp.seg_start[b + 1] - sp.seg_start[a]) + cband * (b - a);
@@ -547,6 +565,7 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   a.ppitch = p->ppitch;
   a.pt_bufs = p->pt_bufs;
   a.packed = p->packed;
+  a.threads = p->threads;
   a.mel_mma = p->mel_mma;
   a.m_tiles = (p->TF + 15) / 16;
   a.mma_n_pairs = p->mma_n_pairs;

@@ -44,6 +44,7 @@ struct StftArgs {
   const int* mma_units;  // [8][16] (n | m << 8) units of each warp, -1 terminated
   int early_tma;         // single span buffer: prefetch the next tile right after the load phase (extra barrier)
   int debug_skip;        // profiling aid (MMF_DEBUG_SKIP): bit 0 skips the FFT phase, bit 1 the mel phase
+  int threads;           // CTA size: 256 (two CTAs per SM) or 512 (one)
   int packed;            // two frames per thread group on packed FP32 instructions (FFMA2/FADD2)
   int n_mels;
   float amin;
@@ -64,10 +65,10 @@ struct StftGeometry {
 };
 
 bool stft_packed_supported(int n_fft);
-int stft_geometry(int n_fft, int packed, StftGeometry* g);
+int stft_geometry(int n_fft, int packed, int threads, StftGeometry* g);
 size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int n_tiles);
 size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed,
-                       size_t mel_tab_bytes);
+                       size_t mel_tab_bytes, int threads);
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
                             cudaStream_t st);
 
@@ -160,7 +161,7 @@ struct mmf_plan {
   int sm_count;
   mmf::StftGeometry geo;
   // tile geometry
-  int TF, ppitch, pt_bufs, span_bufs, ctas_per_sm, lead, packed, mel_mma;
+  int TF, ppitch, pt_bufs, span_bufs, ctas_per_sm, lead, packed, mel_mma, threads = 256;
   size_t smem;
   // device constants
   float* d_window = nullptr;

@@ -121,9 +121,12 @@ constexpr int kMaxUnits = 16;  // (n-tile, m-tile) units per warp: n_mels <= 512
 
 // V = float2: one frame per thread group; V = c2: two adjacent frames per thread group on
 // packed FP32 instructions (fft_regs.cuh)
-template <int NFFT, typename V>
-__global__ void __launch_bounds__(kThreads, 2)
+// THREADS = 256: two CTAs per SM; THREADS = 512: one CTA per SM with twice the warps, for
+// configurations (large n_fft) whose tiles leave room for only one CTA
+template <int NFFT, typename V, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
     stft_mel_kernel(const __grid_constant__ CUtensorMap tmap, const StftArgs p) {
+  constexpr int kThreads = THREADS;  // (shadows the file-level default inside the kernel)
   using C = FftCfg<NFFT>;
   using TR = CxTraits<V>;
   using Tw = typename TR::Tw;
@@ -474,9 +477,10 @@ size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int
 }
 
 template <int NFFT>
-static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed, size_t mel_tab_bytes) {
+static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed, size_t mel_tab_bytes,
+                           int threads) {
   using C = FftCfg<NFFT>;
-  constexpr int SLOTS = kThreads / C::TPF;
+  const int SLOTS = threads / C::TPF;
   constexpr int FP = (C::F + 7) & ~7;
   const size_t tw_bytes = packed ? sizeof(c2) : sizeof(float2);
   size_t b = 0;
@@ -491,10 +495,10 @@ static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_buf
 }
 
 template <int NFFT>
-static void geometry_t(StftGeometry* g, int packed) {
+static void geometry_t(StftGeometry* g, int packed, int threads) {
   using C = FftCfg<NFFT>;
   g->tpf = C::TPF;
-  g->fpi = (kThreads / C::TPF) * (packed ? 2 : 1);
+  g->fpi = (threads / C::TPF) * (packed ? 2 : 1);
   g->tw1 = C::TW1;
   g->tw2 = C::TW2;
   g->r3 = C::R3;
@@ -504,50 +508,49 @@ static void geometry_t(StftGeometry* g, int packed) {
 // two frames per thread group need <= 32 frames per iteration (one frame per lane in the mel phase)
 bool stft_packed_supported(int n_fft) { return n_fft >= 512; }
 
-int stft_geometry(int n_fft, int packed, StftGeometry* g) {
+int stft_geometry(int n_fft, int packed, int threads, StftGeometry* g) {
   switch (n_fft) {
-    case 256: geometry_t<256>(g, packed); return 0;
-    case 512: geometry_t<512>(g, packed); return 0;
-    case 1024: geometry_t<1024>(g, packed); return 0;
-    case 2048: geometry_t<2048>(g, packed); return 0;
-    case 4096: geometry_t<4096>(g, packed); return 0;
+    case 256: geometry_t<256>(g, packed, threads); return 0;
+    case 512: geometry_t<512>(g, packed, threads); return 0;
+    case 1024: geometry_t<1024>(g, packed, threads); return 0;
+    case 2048: geometry_t<2048>(g, packed, threads); return 0;
+    case 4096: geometry_t<4096>(g, packed, threads); return 0;
     default: return -1;
   }
 }
 
 size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed,
-                       size_t mel_tab_bytes) {
+                       size_t mel_tab_bytes, int threads) {
   switch (n_fft) {
-    case 256: return smem_bytes_t<256>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
-    case 512: return smem_bytes_t<512>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
-    case 1024: return smem_bytes_t<1024>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
-    case 2048: return smem_bytes_t<2048>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
-    case 4096: return smem_bytes_t<4096>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes);
+    case 256: return smem_bytes_t<256>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
+    case 512: return smem_bytes_t<512>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
+    case 1024: return smem_bytes_t<1024>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
+    case 2048: return smem_bytes_t<2048>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
+    case 4096: return smem_bytes_t<4096>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
     default: return 0;
   }
 }
 
-template <int NFFT, typename V>
+template <int NFFT, typename V, int THREADS>
 static cudaError_t launch_v(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e =
-        cudaFuncSetAttribute(stft_mel_kernel<NFFT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
-  }
-  stft_mel_kernel<NFFT, V><<<grid, kThreads, smem, st>>>(tmap, a);
+  auto kfn = stft_mel_kernel<NFFT, V, THREADS>;
+  MMF_SMEM_ONCE(kfn, 227 * 1024);
+  kfn<<<grid, THREADS, smem, st>>>(tmap, a);
   return cudaGetLastError();
 }
 
 template <int NFFT>
 static cudaError_t launch_t(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
-  if constexpr (NFFT >= 512) {
-    if (a.packed) return launch_v<NFFT, c2>(tmap, a, grid, smem, st);
+  if constexpr (NFFT >= 1024) {  // 512-thread CTAs exist for the sizes that can need them
+    if (a.threads == 512) {
+      if (a.packed) return launch_v<NFFT, c2, 512>(tmap, a, grid, smem, st);
+      return launch_v<NFFT, float2, 512>(tmap, a, grid, smem, st);
+    }
   }
-  return launch_v<NFFT, float2>(tmap, a, grid, smem, st);
+  if constexpr (NFFT >= 512) {
+    if (a.packed) return launch_v<NFFT, c2, 256>(tmap, a, grid, smem, st);
+  }
+  return launch_v<NFFT, float2, 256>(tmap, a, grid, smem, st);
 }
 
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
