@@ -508,3 +508,60 @@ def test_find_peaks_matches_scipy(cuda_device):
     idx, cnt = plan.find_peaks(x[0], max_peaks=3)
     ref, _ = scipy.signal.find_peaks(x[0])
     assert int(cnt[0]) == len(ref) and np.array_equal(idx[0].cpu().numpy(), ref[:3])
+
+
+GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden")
+GOLDEN_CASES = {
+    # name: (seed, sr, seconds, kwargs) -- the recipe of tests/golden/make_golden.py
+    "cfg1_16k_40mel": (0, 16000, 2.0, dict(tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)),
+    "cfg3_44k_128mel": (1, 44100, 1.0, dict(tStep=0.01, winLen=0.025, n_fft=2048, n_mels=128, n_mfcc=20)),
+    "gui_default_10k": (2, 10000, 2.0, dict(tStep=0.005, winLen=0.025, n_fft=512, n_mels=128, n_mfcc=13, fmin=100, fmax=10000)),
+    "cfg4_long_hop": (3, 16000, 4.0, dict(tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13, mod_hop_s=0.01)),
+}
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_cuda_path_against_committed_golden_vectors(name, cuda_device):
+    """The CUDA path against the committed fixtures themselves (no oracle call at test time)."""
+    import os
+
+    seed, sr, secs, kw = GOLDEN_CASES[name]
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    y = synth_clip(seed, int(sr * secs), sr)
+    assert np.array_equal(y[:64], g["y_head"]) and len(y) == int(g["n"])
+    res = mm.mfcc_features_batch(y[None, :], sr, **kw)
+    assert np.array_equal(res["T"], g["T"])
+    # clamped log-mel: absolute dB bound equivalent to 1e-4 relative on linear power
+    assert np.max(np.abs(res["logmel"][0] - g["logmel"])) < 4.4e-4
+    assert np.max(np.abs(res["mfcc"][0] - g["mfcc"])) < ABS_TOL
+    assert np.max(np.abs(res["delta"][0] - g["delta"])) < ABS_TOL
+    assert np.max(np.abs(res["totChange"][0] - g["totChange"])) < ABS_TOL
+    step = 10 if name == "cfg4_long_hop" else 1
+    ms = res["modspec"][0][:, ::step]
+    assert ms.shape == g["modspec"].shape
+    assert np.max(np.abs(ms - g["modspec"])) < 5e-3 * max(1.0, float(np.abs(g["modspec"]).max()) / 100.0)
+    be = res["band_energy"][0]
+    assert np.max(np.abs(be - g["band_energy"]) / np.maximum(1.0, np.abs(g["band_energy"]))) < 2e-3
+
+
+def test_cuda_path_against_golden_edge_cases(cuda_device):
+    import os
+
+    g = np.load(os.path.join(GOLDEN_DIR, "edge_cases.npz"))
+    n, sr = 8000, 16000
+    t = np.arange(n) / sr
+    z = np.zeros(n, np.float32)
+    imp0, impN = z.copy(), z.copy()
+    imp0[0], impN[-1] = 1.0, 1.0
+    clips = {"zero": z, "dc": np.full(n, 0.25, np.float32), "tone_bin20": (0.5 * np.sin(2 * np.pi * (sr / 512 * 20) * t)).astype(np.float32),
+             "impulse_first": imp0, "impulse_last": impN}
+    cfg = mm.MfccConfig(sr, 512, 400, 160, 40, 13, 0.0, 8000.0)
+    plan = mm.get_plan(cfg)
+    for k, y in clips.items():
+        lm, cmax = plan.logmel(y[None, :])
+        mf = plan.mfcc(lm, cmax).cpu().numpy()[0]
+        assert np.max(np.abs(mf - g[k + "_mfcc"])) < ABS_TOL, k
+    y22 = synth_clip(9, 21 * 50, 10000)
+    kw = dict(tStep=0.005, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=100, maxFreq=10000, outFiltCutOff=[12])
+    tot, T = mm.get_MFCCS_change(y22, 10000, **kw)
+    assert np.array_equal(T, g["t22_T"]) and np.max(np.abs(tot - g["t22_tot"])) < ABS_TOL
