@@ -185,6 +185,7 @@ _SIGNATURES = {
         [_vp, _vp, _i64, _i64, _i64, C.POINTER(mmf_change_params), C.POINTER(mmf_modspec_params), _vp, _vp, _vp, _vp, _vp],
     ),
     "mmf_pcm16_to_f32": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "mmf_hilbert_envelope": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "mmf_find_peaks": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "mmf_resample_poly": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _vp]),
     "mmf_abi_sizeof": (C.c_int, [_i32]),

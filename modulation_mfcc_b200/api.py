@@ -558,8 +558,9 @@ def calculate_amplitude_envelope(
     """Drop-in for ``calculate_amplitude_envelope`` / ``get_amplitude``
     (script/calc.py:221-343, script/mfcc.py:137-259), method ``'RMS'``.
 
-    ``'Hilb'`` (full-length Hilbert transform) and ``'RMSpraat'`` (Praat) are not
-    built yet and raise NotImplementedError -- there is no CPU fallback."""
+    ``'Hilb'`` is the full-length Hilbert envelope (``mmf_hilbert_envelope``); like the reference
+    (lower-case typo at script/calc.py:333) its time axis comes out on the hop grid.  ``'RMSpraat'``
+    (Praat) raises NotImplementedError -- there is no CPU fallback."""
     torch = _torch()
     if method == "RMS":
         frLen = int(hopLen * sr)
@@ -573,8 +574,18 @@ def calculate_amplitude_envelope(
             amp_dev = plan.rms(_to_dev(xa, torch.float32, di), winLenS, frLen, bool(center))[0]
         except MmfError as e:
             _raise_from(e)
-    elif method in ("Hilb", "RMSpraat"):
-        raise NotImplementedError(f"amplitude method {method!r} is outside the B200 hot path (no CPU fallback)")
+    elif method == "Hilb":
+        di = _device_index(device)
+        plan = _any_plan(di)
+        xa = np.asarray(x)
+        if xa.ndim != 1:
+            raise ValueError("calculate_amplitude_envelope (B200): only mono signals are supported")
+        try:
+            amp_dev = plan.hilbert_envelope(_to_dev(xa, torch.float32, di))
+        except MmfError as e:
+            _raise_from(e)
+    elif method == "RMSpraat":
+        raise NotImplementedError("amplitude method 'RMSpraat' calls Praat and is outside the B200 hot path (no CPU fallback)")
     else:
         # the reference falls through with `amp` unbound -> UnboundLocalError (script/calc.py:333)
         raise UnboundLocalError("cannot access local variable 'amp' where it is not associated with a value")

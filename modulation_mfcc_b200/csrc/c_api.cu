@@ -1040,6 +1040,17 @@ int mmf_features_host_pcm16(mmf_plan* plan, const int16_t* pcm16_host, int64_t n
                             delta_host, mag_host, band_host);
 }
 
+int mmf_hilbert_envelope(mmf_plan* plan, const float* x_dev, int64_t n_clips, int64_t n, int64_t x_stride,
+                         float* amp_dev, int64_t amp_stride, void* stream) {
+  if (!plan || !x_dev || !amp_dev) return fail(MMF_ERR_INVALID, "NULL argument");
+  if (n_clips < 1 || n < 1 || n > (1L << 24)) return fail(MMF_ERR_UNSUPPORTED, "need 1 <= n <= 2^24 samples");
+  MMF_CUDA(cudaSetDevice(plan->cfg.device));
+  cudaError_t e = hilbert_envelope_launch(x_dev, n_clips, n, x_stride, amp_dev, amp_stride, plan->sm_count,
+                                          (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "hilbert kernels launch");
+  return MMF_OK;
+}
+
 int mmf_find_peaks(mmf_plan* plan, const double* x_dev, int64_t rows, int64_t T, int64_t row_stride, int32_t minima,
                    int32_t max_peaks, int32_t* idx_dev, int32_t* count_dev, void* stream) {
   if (!plan || !x_dev || !idx_dev || !count_dev) return fail(MMF_ERR_INVALID, "NULL argument");

@@ -371,6 +371,23 @@ class Plan:
         )
         return out
 
+    def hilbert_envelope(self, x):
+        """``np.abs(scipy.signal.hilbert(x))`` along the last axis, float32 on the device."""
+        torch = _torch()
+        x = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
+        x = x.to(device=torch.device("cuda", self.cfg.device), dtype=torch.float32)
+        squeeze = x.ndim == 1
+        if squeeze:
+            x = x[None, :]
+        x = x.contiguous()
+        amp = torch.empty_like(x)
+        check(
+            _lib.lib().mmf_hilbert_envelope(
+                self._h, x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), amp.data_ptr(), amp.stride(0), _stream_ptr(x.device)
+            )
+        )
+        return amp[0] if squeeze else amp
+
     def find_peaks(self, x, *, minima: bool = False, max_peaks: int | None = None):
         """``scipy.signal.find_peaks(x)`` (default arguments) for every float64 row of ``x`` on the
         device.  Returns ``(idx [rows, max_peaks] int32, count [rows] int32)``; row ``r`` holds its

@@ -565,3 +565,18 @@ def test_cuda_path_against_golden_edge_cases(cuda_device):
     kw = dict(tStep=0.005, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=100, maxFreq=10000, outFiltCutOff=[12])
     tot, T = mm.get_MFCCS_change(y22, 10000, **kw)
     assert np.array_equal(T, g["t22_T"]) and np.max(np.abs(tot - g["t22_tot"])) < ABS_TOL
+
+
+@pytest.mark.parametrize("n", [16000, 12345, 4097, 100])
+def test_hilbert_envelope_matches_scipy(n, cuda_device):
+    """'Hilb' amplitude (script/calc.py:284-286): |scipy.signal.hilbert(x)|, even and odd lengths."""
+    x = synth_clip(13, n, 16000)
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    amp = plan.hilbert_envelope(x).cpu().numpy()
+    ref = np.abs(scipy.signal.hilbert(x.astype(np.float64)))
+    assert amp.shape == ref.shape
+    assert np.max(np.abs(amp - ref)) < 1e-4
+    if n == 16000:
+        a, t = mm.calculate_amplitude_envelope(x, 16000, method="Hilb")
+        ra, rt = oracle.calculate_amplitude_envelope(x, 16000, method="Hilb")
+        assert np.max(np.abs(a - ra)) < 1e-4 and np.array_equal(t, rt)

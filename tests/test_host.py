@@ -186,7 +186,7 @@ def test_argument_validation_happens_before_any_gpu_work():
     with pytest.raises(ValueError, match="Méthode inconnue"):
         mm.get_velocity(x, 1.0, method="bogus")
     with pytest.raises(NotImplementedError):
-        mm.calculate_amplitude_envelope(x, 100.0, method="Hilb")
+        mm.calculate_amplitude_envelope(x, 100.0, method="RMSpraat")
 
 
 def test_stencil_probing_matches_scipy():
