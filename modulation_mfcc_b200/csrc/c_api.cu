@@ -1076,14 +1076,18 @@ int mmf_resample_poly(mmf_plan* plan, const float* x_dev, int64_t n_clips, int64
                       float* y_dev, int64_t y_stride, void* stream) {
   if (!plan || !x_dev || !h_host || !y_dev) return fail(MMF_ERR_INVALID, "NULL argument");
   if (n_clips < 1 || n_clips > 65535 || n_in < 1 || n_out < 1) return fail(MMF_ERR_INVALID, "bad sizes");
-  if (up < 1 || down < 1 || len_h < 1 || (size_t)len_h * 4 > (60u << 10))
-    return fail(MMF_ERR_UNSUPPORTED, "need up, down >= 1 and a filter of at most 15360 taps");
+  if (up < 1 || down < 1 || len_h < 1 || len_h > (1 << 22))
+    return fail(MMF_ERR_UNSUPPORTED, "need up, down >= 1 and a filter of at most 2^22 taps");
   MMF_CUDA(cudaSetDevice(plan->cfg.device));
-  void* h_dev = nullptr;
-  int rc = stage_consts(plan, h_host, (size_t)len_h * 4, 0, &h_dev, (cudaStream_t)stream);
-  if (rc) return rc;
-  cudaError_t e = resample_poly_launch(x_dev, n_clips, n_in, x_stride, (const float*)h_dev, len_h, up, down,
-                                       n_pre_remove, n_out, y_stride, y_dev, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* h_dev = nullptr;  // stream-ordered scratch for the taps (pageable source: the copy is staged, so
+                           // h_host may be reused as soon as this call returns)
+  MMF_CUDA(cudaMallocAsync((void**)&h_dev, (size_t)len_h * 4, st));
+  cudaError_t e = cudaMemcpyAsync(h_dev, h_host, (size_t)len_h * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = resample_poly_launch(x_dev, n_clips, n_in, x_stride, h_dev, len_h, up, down, n_pre_remove, n_out, y_stride,
+                             y_dev, st);
+  cudaFreeAsync(h_dev, st);
   if (e != cudaSuccess) return cuda_fail(e, "resample_poly_kernel launch");
   return MMF_OK;
 }

@@ -452,7 +452,7 @@ def test_pcm16_host_path_is_bit_identical(cuda_device):
     assert np.array_equal(y, f32)
 
 
-@pytest.mark.parametrize("up,down,n", [(160, 441, 44100), (1, 2, 10001), (3, 1, 5000), (441, 160, 8000), (2, 3, 97)])
+@pytest.mark.parametrize("up,down,n", [(160, 441, 44100), (1, 2, 10001), (3, 1, 5000), (441, 160, 8000), (2, 3, 97), (1000, 997, 6000)])
 def test_resample_poly_matches_scipy(up, down, n, cuda_device):
     rng = np.random.default_rng(up * 1000 + down)
     x = rng.standard_normal((3, n)).astype(np.float32)
