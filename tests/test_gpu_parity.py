@@ -580,3 +580,76 @@ def test_hilbert_envelope_matches_scipy(n, cuda_device):
         a, t = mm.calculate_amplitude_envelope(x, 16000, method="Hilb")
         ra, rt = oracle.calculate_amplitude_envelope(x, 16000, method="Hilb")
         assert np.max(np.abs(a - ra)) < 1e-4 and np.array_equal(t, rt)
+
+
+def _random_cases(n_cases=28, seed=2026):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for i in range(n_cases):
+        sr = int(rng.choice([8000, 10000, 16000, 22050, 44100]))
+        n_fft = int(rng.choice([256, 512, 512, 1024, 2048]))
+        win = int(rng.integers(max(16, n_fft // 4), n_fft + 1))
+        hop = int(rng.integers(max(1, win // 8), win + 1))
+        n_mels = int(rng.integers(8, 161))
+        n_mfcc = int(rng.integers(2, min(40, n_mels) + 1))
+        fmin = float(rng.choice([0.0, 50.0, 300.0]))
+        fmax = float(rng.choice([sr / 2, 0.4 * sr, 1.2 * sr]))
+        frames = int(rng.integers(25, 140))
+        n = frames * hop + int(rng.integers(0, hop))
+        clips = int(rng.integers(1, 4))
+        cases.append((i, sr, n_fft, win, hop, n_mels, n_mfcc, fmin, fmax, n, clips))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_cases(), ids=lambda c: f"r{c[0]}_fft{c[2]}_w{c[3]}_h{c[4]}_m{c[5]}")
+def test_randomised_configurations(case, cuda_device):
+    """Seeded sweep over frame geometry and filterbank shapes (odd hops and clip lengths take the
+    non-vector and non-TMA loaders, win == n_fft, fmax above Nyquist, narrow and wide banks)."""
+    i, sr, n_fft, win, hop, n_mels, n_mfcc, fmin, fmax, n, clips = case
+    cfg = mm.MfccConfig(sr, n_fft, win, hop, n_mels, n_mfcc, fmin, fmax)
+    y = synth_batch(200 + 7 * i, clips, n, sr)
+    plan = mm.get_plan(cfg)
+    lm, cmax = plan.logmel(y)
+    lm_unclamped = lm.cpu().numpy().copy()
+    mf, dl = plan.mfcc(lm, cmax, delta=True)
+    mf, dl = mf.cpu().numpy(), dl.cpu().numpy()
+    for c in range(clips):
+        M, inter, unclamped = _oracle_unclamped(y[c], cfg)
+        assert lm_unclamped[c].shape == unclamped.shape
+        assert _mel_rel_err(lm_unclamped[c], unclamped) <= LOGMEL_REL
+        assert np.max(np.abs(mf[c] - M)) < ABS_TOL
+        assert np.max(np.abs(dl[c] - np.gradient(M, axis=1))) < ABS_TOL
+
+
+def _random_change_cases(n_cases=14, seed=77):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_cases):
+        sr = int(rng.choice([10000, 16000]))
+        tStep = float(rng.choice([0.005, 0.01, 0.0125]))
+        kw = dict(
+            tStep=tStep, winLen=0.025, n_mfcc=int(rng.integers(3, 21)), n_fft=512, minFreq=float(rng.choice([0, 100])),
+            maxFreq=float(rng.choice([sr / 2, sr])), removeFirst=int(rng.integers(0, 2)),
+            filtCutoff=float(rng.choice([6, 12, 18])), filtOrd=int(rng.choice([2, 4, 6, 8, 10])),
+            diffMethod=str(rng.choice(["grad", "sg"])), outFilter=rng.choice([None, "iir", "fir", "sg"]),
+            outFiltType=str(rng.choice(["low", "high"])), outFiltCutOff=[float(rng.choice([5, 12, 20]))],
+            outFiltLen=int(rng.choice([3, 5, 6, 7, 9])), outFiltPolyOrd=2, n_mels=int(rng.choice([40, 64, 128])),
+        )
+        if kw["outFilter"] == "fir" and kw["outFiltType"] == "high" and kw["outFiltLen"] % 2 == 0:
+            kw["outFiltLen"] += 1  # scipy refuses an even-length high-pass FIR
+        secs = float(rng.choice([1.5, 4.0, 9.0, 25.0]))  # 25 s at 5 ms steps: rows beyond the shared-memory IIR
+        out.append((i, sr, secs, kw))
+    return out
+
+
+@pytest.mark.parametrize("case", _random_change_cases(), ids=lambda c: f"c{c[0]}")
+def test_randomised_change_pipeline(case, cuda_device):
+    """Seeded sweep over the post-MFCC part of get_MFCCS_change: filter orders (fused kernel up to
+    4 sections, sequential beyond), derivative methods, every output-filter branch, short and long rows."""
+    i, sr, secs, kw = case
+    y = synth_batch(300 + i, 2, int(sr * secs), sr)
+    tot, T = mm.get_MFCCS_change_batch(y, sr, **kw)
+    for c in range(2):
+        ref, Tref = oracle.get_MFCCS_change(y[c], sr, **kw)
+        assert np.array_equal(T, Tref)
+        assert np.max(np.abs(tot[c] - ref)) < ABS_TOL, kw
