@@ -61,6 +61,7 @@ typedef struct {
 #define MMF_FLAG_SPLIT_SMEM 2  /* n_fft = 512: pair bins through shared memory instead of shuffles */
 #define MMF_FLAG_SCALAR_FFT 8     /* one frame per thread group (scalar FP32) instead of two on packed FFMA2/FADD2 */
 #define MMF_FLAG_MMA_MEL 16       /* mel projection on the tensor cores (mma.sync TF32 x3) instead of the sparse FP32 walk */
+#define MMF_FLAG_MMA_DCT 32       /* clamp + DCT-II on the tensor cores (mma.sync TF32 x3) instead of scalar FP32 FMAs */
 #define MMF_FLAG_UNFUSED_CHANGE 4 /* composite calls: separate filter / derivative kernels instead of the fused one */
 
 typedef struct mmf_plan mmf_plan;

@@ -51,6 +51,7 @@ MMF_FLAG_SPLIT_SMEM = 2
 MMF_FLAG_UNFUSED_CHANGE = 4
 MMF_FLAG_SCALAR_FFT = 8
 MMF_FLAG_MMA_MEL = 16
+MMF_FLAG_MMA_DCT = 32
 
 
 class mmf_config(C.Structure):

@@ -77,6 +77,11 @@ cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const i
                         int n_mels, int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place,
                         cudaStream_t st);
 
+void mfcc_mma_bfrag(const float* dct, int n_mfcc, int n_mels, std::vector<float4>& out);
+bool mfcc_mma_supported(int n_mfcc, int n_mels);
+cudaError_t mfcc_mma_launch(const float4* bfrag_dev, float* logmel, const int* clipmax, long n_clips, long T, int n_mels,
+                            int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place, cudaStream_t st);
+
 struct SosArgs {
   int n_sections;
   int padlen;
@@ -181,6 +186,7 @@ struct mmf_plan {
   size_t mel_tab_bytes = 0;
   float2* d_w2 = nullptr;
   float* d_dct = nullptr;  // [n_mels][nc_pad]
+  float4* d_dct_bfrag = nullptr;  // DCT B fragments of the tensor-core MFCC kernel
   int nc_pad = 0;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   // tables of the trajectory FFT, rebuilt when (win, nfft, bands) change

@@ -6,6 +6,7 @@
 // kernel, so they are written for coalesced streaming access, not for math rate.
 #include <cfloat>
 #include <cstdint>
+#include <cstring>
 
 #include "mmf_internal.h"
 
@@ -133,6 +134,178 @@ cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const i
     MMF_MFCC_CASE(128)
   }
 #undef MMF_MFCC_CASE
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K3 on the tensor cores: [frames x n_mels] . [n_mels x n_mfcc] with mma.sync m16n8k8 TF32 and
+// the 3-term operand split (hi*hi + hi*lo + lo*hi into independent fp32 accumulators, ~2^-21
+// relative per product; single-pass TF32 misses the 1e-3 MFCC tolerance by 27x).
+// The FP32 kernel above is bound by instruction issue (83 % of the issue slots, 640 FFMAs per
+// frame); here the contraction is 60 MMAs per 32 frames and the kernel goes back to being a stream.
+//   A (m16 x k8) = clamped log-mel, rows = frames, straight from global memory (each element is
+//                  needed by exactly one lane; 8 consecutive frames per mel row = one 32-byte sector),
+//   B (k8 x n8)  = DCT-II rows, pre-split hi/lo in fragment order in shared memory,
+//   D (m16 x n8) -> a per-warp [NC][34] tile in shared memory, from which MFCC and its np.gradient
+//                  delta leave as coalesced 128-byte rows (one frame of halo on each side).
+// One warp = 32 frames (30 owned + halo) of one clip.
+// ---------------------------------------------------------------------------
+constexpr int kMmaWarps = 4;
+constexpr int kMmaOwn = 30;  // frames owned per warp when the delta is requested (else 32)
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// NT = n-tiles of 8 coefficients (n_mfcc <= 8*NT)
+template <int NT>
+__global__ void __launch_bounds__(kMmaWarps * 32)
+    mfcc_mma_kernel(const float4* __restrict__ bfrag, float* logmel, const int* __restrict__ clipmax, long T, int n_mels,
+                    int n_mfcc, float top_db, float* __restrict__ mfcc, float* __restrict__ delta, int clamp_in_place) {
+  extern __shared__ __align__(16) float sm_mma[];
+  const int ksteps = (n_mels + 7) / 8;
+  float4* s_b = reinterpret_cast<float4*>(sm_mma);                 // [ksteps][NT][32] (hi0, hi1, lo0, lo1)
+  float* s_c = sm_mma + (size_t)ksteps * NT * 32 * 4;              // [kMmaWarps][8*NT][34]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  for (int i = tid; i < ksteps * NT * 32; i += kMmaWarps * 32) s_b[i] = bfrag[i];
+  __syncthreads();
+  const long clip = blockIdx.y;
+  const int halo = delta != nullptr ? 1 : 0;
+  const int own = delta != nullptr ? kMmaOwn : 32;
+  const long t_base = ((long)blockIdx.x * kMmaWarps + warp) * own - halo;  // first frame of this warp's 32
+  if (t_base >= T) return;
+  const float thr = top_db >= 0.0f ? key_to_float(clipmax[clip]) - top_db : -FLT_MAX;
+  float* lm = logmel + (size_t)clip * n_mels * T;
+  float acc[2][NT][3][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][n][q][e] = 0.0f;
+  // frames of this lane's fragment rows: t_base + 16*m + g (+8)
+  for (int ks = 0; ks < ksteps; ++ks) {
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long t = t_base + 16 * m + g + ((e & 1) ? 8 : 0);
+        const int mel = 8 * ks + t4 + ((e & 2) ? 4 : 0);
+        float x = 0.0f;
+        if (t >= 0 && t < T && mel < n_mels) {
+          float* src = lm + (size_t)mel * T + t;
+          x = fmaxf(__ldcs(src), thr);
+          // the clamp is written back by the lanes that own the frame (halo frames belong to a neighbour)
+          if (clamp_in_place && t >= t_base + halo && t < t_base + halo + own) *src = x;
+        }
+        ah[m][e] = __float_as_uint(x) & 0xffffe000u;
+        al[m][e] = __float_as_uint(x - __uint_as_float(ah[m][e]));
+      }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float4 b = s_b[(ks * NT + n) * 32 + lane];
+      const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
+      const uint32_t bl0 = __float_as_uint(b.z), bl1 = __float_as_uint(b.w);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mma_tf32_16x8x8(acc[m][n][0], ah[m], bh0, bh1);
+        mma_tf32_16x8x8(acc[m][n][1], ah[m], bl0, bl1);
+        mma_tf32_16x8x8(acc[m][n][2], al[m], bh0, bh1);
+      }
+    }
+  }
+  // D fragments -> s_c[coef][local frame]: (frame g, coef 2*t4), (g, 2*t4+1), (g+8, 2*t4), (g+8, 2*t4+1)
+  float* c = s_c + (size_t)warp * (8 * NT) * 34;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = acc[m][n][0][e] + (acc[m][n][1][e] + acc[m][n][2][e]);
+        c[(8 * n + 2 * t4 + (e & 1)) * 34 + 16 * m + g + ((e & 2) ? 8 : 0)] = v;
+      }
+  __syncwarp();
+  // lane = local frame; owned frames leave as coalesced rows
+  const long t = t_base + lane;
+  const bool mine = lane >= halo && lane < halo + own && t < T;
+  if (mine) {
+    for (int j = 0; j < n_mfcc; ++j) {
+      const float* cj = c + j * 34 + lane;
+      mfcc[((size_t)clip * n_mfcc + j) * T + t] = cj[0];
+      if (delta != nullptr) {
+        float d;
+        if (T == 1) {
+          d = 0.0f;
+        } else if (t == 0) {
+          d = cj[1] - cj[0];
+        } else if (t == T - 1) {
+          d = cj[0] - cj[-1];
+        } else {
+          d = (cj[1] - cj[-1]) / 2.0f;
+        }
+        delta[((size_t)clip * n_mfcc + j) * T + t] = d;
+      }
+    }
+  }
+}
+
+// B fragments of the DCT for the MMA kernel: [ksteps][NT][32 lanes] (hi0, hi1, lo0, lo1);
+// b0 = D[coef 8n + lane/4][mel 8ks + lane%4], b1 = ... mel + 4
+void mfcc_mma_bfrag(const float* dct /* [n_mfcc][n_mels] */, int n_mfcc, int n_mels, std::vector<float4>& out) {
+  const int ksteps = (n_mels + 7) / 8, NT = (n_mfcc + 7) / 8;
+  out.assign((size_t)ksteps * NT * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+  auto at = [&](int coef, int mel) { return (coef < n_mfcc && mel < n_mels) ? dct[(size_t)coef * n_mels + mel] : 0.0f; };
+  auto hi = [](float w) {
+    uint32_t u;
+    memcpy(&u, &w, 4);
+    u &= 0xffffe000u;
+    float h;
+    memcpy(&h, &u, 4);
+    return h;
+  };
+  for (int ks = 0; ks < ksteps; ++ks)
+    for (int n = 0; n < NT; ++n)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t4 = lane & 3;
+        const float w0 = at(8 * n + g, 8 * ks + t4), w1 = at(8 * n + g, 8 * ks + t4 + 4);
+        const float h0 = hi(w0), h1 = hi(w1);
+        out[((size_t)ks * NT + n) * 32 + lane] = make_float4(h0, h1, w0 - h0, w1 - h1);
+      }
+}
+
+bool mfcc_mma_supported(int n_mfcc, int n_mels) { return n_mfcc <= 32 && n_mels <= 512; }
+
+cudaError_t mfcc_mma_launch(const float4* bfrag_dev, float* logmel, const int* clipmax, long n_clips, long T, int n_mels,
+                            int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place, cudaStream_t st) {
+  const int NT = (n_mfcc + 7) / 8, ksteps = (n_mels + 7) / 8;
+  const int own = delta != nullptr ? kMmaOwn : 32;
+  const long per_block = (long)kMmaWarps * own;
+  dim3 grid((unsigned)((T + (delta != nullptr ? 1 : 0) + per_block - 1) / per_block), (unsigned)n_clips);
+  const size_t smem = (size_t)ksteps * NT * 32 * 16 + (size_t)kMmaWarps * 8 * NT * 34 * 4;
+#define MMF_MMA_CASE(N)                                                                                          \
+  case N: {                                                                                                      \
+    MMF_SMEM_ONCE(mfcc_mma_kernel<N>, 200 * 1024);                                                               \
+    mfcc_mma_kernel<N><<<grid, kMmaWarps * 32, smem, st>>>(bfrag_dev, logmel, clipmax, T, n_mels, n_mfcc, top_db, \
+                                                         mfcc, delta, clamp_in_place);                           \
+    break;                                                                                                       \
+  }
+  switch (NT) {
+    MMF_MMA_CASE(1)
+    MMF_MMA_CASE(2)
+    MMF_MMA_CASE(3)
+    MMF_MMA_CASE(4)
+    default: return cudaErrorInvalidValue;
+  }
+#undef MMF_MMA_CASE
   count_launch();
   return cudaGetLastError();
 }

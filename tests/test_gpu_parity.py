@@ -102,6 +102,22 @@ def test_logmel_mfcc_delta(name, cuda_device):
         assert np.max(np.abs(dl[i] - np.gradient(M, axis=1))) < ABS_TOL, name
 
 
+@pytest.mark.parametrize("name", ["cfg1_16k", "gui_default", "cfg3_44k", "n256"])
+def test_mfcc_tensor_core_variant(name, cuda_device):
+    """MMF_FLAG_MMA_DCT: clamp + DCT-II (+ delta) through mma.sync TF32 x3 instead of FP32 FMAs."""
+    cfg, secs = _cfg(name, flags=_lib.MMF_FLAG_MMA_DCT)
+    y = synth_batch(60, 2, int(cfg.sample_rate * secs), cfg.sample_rate)
+    plan = mm.get_plan(cfg)
+    lm, cmax = plan.logmel(y)
+    mf, dl = plan.mfcc(lm, cmax, delta=True)
+    lm, mf, dl = lm.cpu().numpy(), mf.cpu().numpy(), dl.cpu().numpy()
+    for i in range(2):
+        M, inter, _ = _oracle_unclamped(y[i], cfg)
+        assert np.max(np.abs(mf[i] - M)) < ABS_TOL
+        assert np.max(np.abs(dl[i] - np.gradient(M, axis=1))) < ABS_TOL
+        assert np.max(np.abs(lm[i] - inter["logmel"])) < 4.4e-4  # clamped in place
+
+
 def test_clamp_is_active_on_gui_default(cuda_device):
     """fmax above Nyquist leaves empty mel filters at -100 dB, so top_db=80 always clamps."""
     cfg, secs = _cfg("gui_default")

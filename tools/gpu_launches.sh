@@ -4,7 +4,7 @@ tag=${1:-run}
 mkdir -p gpurun_out
 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/plain_$tag.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-  -k regex:"mfcc_kernel|sosfilt|delta_norm|modspec|stft_mel|fill_i32|change_fused" -s 20 -c 8 --csv \
+  -k regex:"mfcc|pcm16|sosfilt|delta_norm|modspec|stft_mel|fill_i32|change_fused" -s 20 -c 8 --csv \
   --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_$tag.log 2>&1
 echo rc=$?
 python - <<PY
