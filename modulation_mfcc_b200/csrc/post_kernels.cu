@@ -1,6 +1,9 @@
-// K3-K6 and the small filters around them: everything after the log-mel
-// spectrogram in get_MFCCS_change (script/mfcc.py:387-425) plus the helpers of
-// script/calc.py on the same path (get_velocity, RMS envelope).
+// K3 and the generic kernels around the path: clamp + DCT-II (+ delta) in FP32 and on the
+// tensor cores, the sequential zero-phase IIR (the chunk-parallel and fused forms live in
+// change_fused.cu), derivative + norm, FIR filtfilt, stencils (get_velocity, Savitzky-Golay),
+// the generic modulation-spectrum kernel (the fast ones live in modspec_fast.cu), RMS and
+// Hilbert envelopes, find_peaks, PCM16 ingest and the polyphase resampler
+// (script/mfcc.py:373-425, script/calc.py:221-343, :593-650; script/main.py:1566, :1601).
 //
 // These stages move ~0.3 MB per clip against 0.64 MB of PCM for the fused STFT
 // kernel, so they are written for coalesced streaming access, not for math rate.

@@ -5,20 +5,24 @@
 // filters.mel + einsum, power_to_db before the top_db clamp).
 //
 // Execution model (sm_100a):
-//  * persistent CTAs (2 per SM, 256 threads), each looping over tiles of TF
-//    consecutive frames of one clip;
+//  * persistent CTAs (2 per SM x 256 threads; 1 x 512 where only one fits), each
+//    looping over tiles of TF consecutive frames of one clip (TF = 32 when it fits);
 //  * the PCM span of a tile ((TF-1)*hop + n_fft samples, hop windows overlap) is
-//    brought in once by TMA (cp.async.bulk.tensor, 1 KB boxes, double buffered,
-//    mbarrier completion); out-of-range coordinates are zero-filled by the TMA
-//    unit, which *is* librosa's center=True / pad_mode='constant' padding, so no
-//    padded copy of the audio ever exists;
-//  * FFT data lives in registers (16 complex points per thread), Hann window in
-//    registers, one shared-memory exchange between radix-16 passes, and for
-//    n_fft = 512 the real-FFT split step pairs bins with warp shuffles;
+//    brought in once by TMA (cp.async.bulk.tensor, 1 KB boxes, mbarrier
+//    completion); out-of-range coordinates are zero-filled by the TMA unit, which
+//    *is* librosa's center=True / pad_mode='constant' padding, so no padded copy
+//    of the audio ever exists.  With one span buffer the next tile's TMA is issued
+//    as soon as every warp holds its frames in registers and streams in under the
+//    transform and the mel projection;
+//  * FFT data lives in registers, 16 complex points per thread -- by default of TWO
+//    adjacent frames at once, packed for FADD2/FMUL2/FFMA2 (fft_regs.cuh) -- with
+//    one shared-memory exchange between radix-16 passes; for n_fft = 512 the
+//    real-FFT split step pairs bins with warp shuffles;
 //  * the power tile stays in shared memory and is projected on the (sparse,
-//    two-slopes-per-bin) mel filterbank by all warps, log'd and streamed out
-//    with coalesced stores; the 1 MB/clip power spectrum never touches HBM
-//    unless the caller asks for it (mmf_stft_power).
+//    two-slopes-per-bin) mel filterbank by all warps, one frame per lane, band
+//    groups balanced on the host (optionally on the tensor cores: mma.sync TF32 x3),
+//    log'd and streamed out with coalesced stores; the 1 MB/clip power spectrum
+//    never touches HBM unless the caller asks for it (mmf_stft_power).
 #include <cfloat>
 #include <cstdint>
 
