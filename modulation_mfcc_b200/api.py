@@ -33,6 +33,21 @@ from .plan import MfccConfig, Plan, frame_sizes, get_plan, make_change_params
 MODULATION_BANDS_HZ = ((0.5, 2.0), (2.0, 4.0), (4.0, 8.0), (8.0, 16.0), (16.0, 32.0))
 
 
+@lru_cache(maxsize=64)
+def _butter_sos_cached(order, wn, btype):
+    return scipy.signal.butter(order, wn if not isinstance(wn, tuple) else list(wn), btype=btype, output="sos")
+
+
+def _butter_sos(order, wn, btype):
+    """``scipy.signal.butter(order, wn, btype, output='sos')`` with the design cached: the GUI calls the
+    path with the same filter over and over, and the design costs as much as the whole GPU pass."""
+    try:
+        key = tuple(float(v) for v in wn) if np.ndim(wn) else float(wn)
+        return _butter_sos_cached(int(order), key, str(btype)).copy()
+    except TypeError:  # unhashable / odd arguments: let scipy validate them
+        return scipy.signal.butter(order, wn, btype=btype, output="sos")
+
+
 def _torch():
     import torch
 
@@ -196,7 +211,7 @@ def _apply_filter_dev(plan: Plan, x_dev, sr, *, filt, cutOff, filtLen, filtType,
             if coeffs is None:
                 w = cutOff / (sr / 2)
                 if ok:
-                    sos = scipy.signal.butter(filtLen, w, btype=filtType, output="sos")
+                    sos = _butter_sos(filtLen, w, filtType)
                 else:
                     raise Exception(
                         "only one or two cut off frequencies allowed. If two freqs are provided, filtType must be bandpass"
@@ -356,7 +371,7 @@ def get_MFCCS_change_batch(
     torch = _torch()
     plan = _change_setup(sigSr, tStep, winLen, n_mfcc, n_fft, minFreq, maxFreq, n_mels, preemph, device, flags)
     cutOffNorm = filtCutoff / ((1 / tStep) / 2)  # script/mfcc.py:398
-    sos = scipy.signal.butter(filtOrd, cutOffNorm, btype="low", output="sos")  # script/mfcc.py:400
+    sos = _butter_sos(filtOrd, cutOffNorm, "low")  # script/mfcc.py:400
     method = 0 if diffMethod == "grad" else 1
     on_device = isinstance(audio, torch.Tensor) and audio.is_cuda
 
@@ -420,7 +435,7 @@ def _design_iir(sr, cutOff, filtLen, filtType):
     if ((len(cutOff) == 1) and ((filtType == "lowpass") | (filtType == "highpass"))) | (
         (len(cutOff) == 2) and (filtType == "bandpass")
     ):
-        return scipy.signal.butter(filtLen, w, btype=filtType, output="sos")
+        return _butter_sos(filtLen, w, filtType)
     raise Exception("only one or two cut off frequencies allowed. If two freqs are provided, filtType must be bandpass")
 
 
@@ -652,7 +667,7 @@ class FeatureExtractor:
     ):
         self.sr, self.tStep, self.winLen = float(sr), float(tStep), float(winLen)
         self.plan = _change_setup(sr, tStep, winLen, n_mfcc, n_fft, fmin, sr / 2 if fmax is None else fmax, n_mels, preemph, device, flags)
-        sos = scipy.signal.butter(filtOrd, filtCutoff / ((1 / tStep) / 2), btype="low", output="sos")
+        sos = _butter_sos(filtOrd, filtCutoff / ((1 / tStep) / 2), "low")
         self.prm = make_change_params(sos, remove_first=removeFirst, diff_method=0, out_sos=sos)
         self.mod_win_s, self.mod_hop_s, self.bands_hz = mod_win_s, mod_hop_s, bands_hz
         self.frame_rate = 1.0 / tStep
