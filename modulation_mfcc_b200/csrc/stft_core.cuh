@@ -376,9 +376,11 @@ MMF_HD void mel_column(const float* pcol, int ppitch, const int* seg_start, cons
   int k = seg_start[m0];
   const float* pp = pcol + k * pitch;
   const float2* wp = w2 + k;
+  int k_next = seg_start[m0 + 1];  // segment bounds are fetched one segment ahead of their use
 #pragma unroll 1
   for (int j = m0; j <= m1; ++j) {
-    const int n = seg_start[j + 1] - k;
+    const int n = k_next - k;
+    k_next = seg_start[j + 2 <= m1 + 1 ? j + 2 : m1 + 1];
     k += n;
     float acc_dn = 0.0f, acc_up = 0.0f;
     int i = 0;
