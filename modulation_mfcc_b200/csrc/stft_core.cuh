@@ -107,9 +107,8 @@ MMF_HD void ph_load(float2 (&v)[16], const float* span, int frame_off, int hop, 
   }
 }
 
-// Two frames (frame_off and frame_off + hop): the window multiply runs on the
-// (re, im) pairs as loaded (one packed multiply per frame and point), then the
-// halves are regrouped into (A.re, B.re), (A.im, B.im).
+// Two frames (frame_off and frame_off + hop): windowed samples land directly in
+// the packed halves (A.re, B.re), (A.im, B.im).
 template <int NFFT, bool VEC>
 MMF_HD void ph_load(c2 (&v)[16], const float* span, int frame_off, int hop, int tau, const float2 (&wreg)[16]) {
   using C = FftCfg<NFFT>;
@@ -126,9 +125,8 @@ MMF_HD void ph_load(c2 (&v)[16], const float* span, int frame_off, int hop, int 
       b.x = span[frame_off + hop + 2 * c];
       b.y = span[frame_off + hop + 2 * c + 1];
     }
-    const pk w = pmake(wreg[n2].x, wreg[n2].y);
-    const pk pa = smul(pmake(a.x, a.y), w), pb = smul(pmake(b.x, b.y), w);
-    v[n2] = CxTraits<c2>::make(pmake(plo(pa), plo(pb)), pmake(phi(pa), phi(pb)));
+    // scalar window products written straight into the packed halves (no regrouping moves)
+    v[n2] = CxTraits<c2>::make(pmake(a.x * wreg[n2].x, b.x * wreg[n2].x), pmake(a.y * wreg[n2].y, b.y * wreg[n2].y));
   }
 }
 
