@@ -669,3 +669,20 @@ def test_randomised_change_pipeline(case, cuda_device):
         ref, Tref = oracle.get_MFCCS_change(y[c], sr, **kw)
         assert np.array_equal(T, Tref)
         assert np.max(np.abs(tot[c] - ref)) < ABS_TOL, kw
+
+
+def test_zero_phase_filter_properties_full_size(cuda_device):
+    """Size-independent property of K4 at the bench's row count (12 288 rows x 1001 frames): linearity
+    (odd extension, zi * x[0] start-up and both passes are linear in x), plus a scipy sample."""
+    torch = _torch()
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    x = torch.randn((12288, 1001), device=cuda_device, dtype=torch.float64, generator=g).cumsum(dim=-1)
+    y = torch.randn((12288, 1001), device=cuda_device, dtype=torch.float64, generator=g)
+    sos = scipy.signal.butter(6, 0.24, output="sos")
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    fx, fy = plan.sosfiltfilt(x, sos), plan.sosfiltfilt(y, sos)
+    fz = plan.sosfiltfilt(2.0 * x - 3.0 * y, sos)
+    scale = float(x.abs().max())
+    assert float((fz - (2.0 * fx - 3.0 * fy)).abs().max()) < 1e-9 * scale
+    ref = scipy.signal.sosfiltfilt(sos, x[:3].cpu().numpy())
+    assert np.max(np.abs(fx[:3].cpu().numpy() - ref)) < 1e-9 * scale
