@@ -266,8 +266,15 @@ static cudaError_t long_launch_ns(const TIn* x, long rows, long T, long xs, int 
   double *fwd = nullptr, *e0 = nullptr, *sin_ = nullptr;
   cudaError_t e;
   if ((e = cudaMallocAsync((void**)&fwd, (size_t)rows * L * 8, st)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&e0, (size_t)units * D * 8, st)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&sin_, (size_t)units * D * 8, st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&e0, (size_t)units * D * 8, st)) != cudaSuccess) {
+    cudaFreeAsync(fwd, st);
+    return e;
+  }
+  if ((e = cudaMallocAsync((void**)&sin_, (size_t)units * D * 8, st)) != cudaSuccess) {
+    cudaFreeAsync(fwd, st);
+    cudaFreeAsync(e0, st);
+    return e;
+  }
   const unsigned grid = (unsigned)((units + kLongWarps - 1) / kLongWarps);
   const unsigned cgrid = (unsigned)((rows + 63) / 64);
   const size_t smem = (size_t)kLongWarps * S * 8;

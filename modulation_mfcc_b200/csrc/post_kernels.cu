@@ -1001,7 +1001,10 @@ cudaError_t hilbert_envelope_launch(const float* x, long n_clips, long n, long s
   ksplit = ksplit < 1 ? 1 : (ksplit > max_split ? max_split : (ksplit > 64 ? 64 : ksplit));
   cudaError_t e;
   if ((e = cudaMallocAsync((void**)&g, (size_t)n * 4, st)) != cudaSuccess) return e;
-  if ((e = cudaMallocAsync((void**)&partial, (size_t)ksplit * n * 8, st)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void**)&partial, (size_t)ksplit * n * 8, st)) != cudaSuccess) {
+    cudaFreeAsync(g, st);
+    return e;
+  }
   hilbert_kernel_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, g);
   count_launch();
   for (long c = 0; c < n_clips; ++c) {
