@@ -63,6 +63,9 @@ typedef struct {
 #define MMF_FLAG_MMA_MEL 16       /* mel projection on the tensor cores (mma.sync TF32 x3) instead of the sparse FP32 walk */
 #define MMF_FLAG_MMA_DCT 32       /* clamp + DCT-II on the tensor cores (mma.sync TF32 x3) instead of scalar FP32 FMAs */
 #define MMF_FLAG_UNFUSED_CHANGE 4 /* composite calls: separate filter / derivative kernels instead of the fused one */
+#define MMF_FLAG_SEPARATE_MFCC 64 /* composite calls: clamp + DCT-II always as its own kernel */
+#define MMF_FLAG_FOLD_MFCC 128    /* composite calls: clamp + DCT-II inside the per-clip kernel even when delta is wanted
+                                     (default: folded only when no delta output is requested; measured in DESIGN.md) */
 
 typedef struct mmf_plan mmf_plan;
 

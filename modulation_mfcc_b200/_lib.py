@@ -52,6 +52,8 @@ MMF_FLAG_UNFUSED_CHANGE = 4
 MMF_FLAG_SCALAR_FFT = 8
 MMF_FLAG_MMA_MEL = 16
 MMF_FLAG_MMA_DCT = 32
+MMF_FLAG_SEPARATE_MFCC = 64
+MMF_FLAG_FOLD_MFCC = 128
 
 
 class mmf_config(C.Structure):

@@ -844,17 +844,32 @@ static int run_post(mmf_plan* p, unsigned char*& cur, float* logmel, const int* 
   if (prm->out_kind == 0 && (rc = fill_sos(prm->out_sos, prm->out_n_sections, &so))) return rc;
   if (T <= sa.padlen) return too_short(sa.padlen);
   if (prm->out_kind == 0 && T <= so.padlen) return too_short(so.padlen);
+  SosPar pa, po;
+  size_t fsmem = 0;
+  const bool out_iir = prm->out_kind == 0;
+  const bool par_ok = !(c.flags & MMF_FLAG_UNFUSED_CHANGE) && sos_par_fill(sa, T, &pa) &&
+                      (!out_iir || sos_par_fill(so, T, &po));
+  // one kernel per clip from log-mel to the curve: clamp + DCT-II (K3) feed the float64 row buffers in
+  // shared memory directly; MFCC / delta go to HBM only if the caller asked for them.  Measured on the
+  // bench workload: 1 % faster than the separate MFCC kernel without a delta output, 1 % slower with
+  // one when the modulation spectrum follows -- hence the default.
+  const bool fold = (c.flags & MMF_FLAG_FOLD_MFCC) || delta_out == nullptr;
+  if (par_ok && fold && !(c.flags & (MMF_FLAG_SEPARATE_MFCC | MMF_FLAG_MMA_DCT)) && n_clips <= 0x7fffffff &&
+      change_fused_lm_supported(pa, out_iir ? &po : nullptr, c.n_mfcc, c.n_mels, first, rows, T, &fsmem)) {
+    const FusedMfccArgs lm{p->d_dct, p->nc_pad, logmel, clipmax, c.n_mels, c.top_db, mfcc_out, delta_out,
+                           clamp_in_place};
+    cudaError_t e = change_fused_launch(nullptr, n_clips, c.n_mfcc, first, rows, T, prm->diff_method, pa,
+                                        out_iir ? po : pa, prm->out_kind, tot, fsmem, &lm, st);
+    if (e == cudaSuccess) return MMF_OK;
+    if (e != cudaErrorNotSupported) return cuda_fail(e, "change_fused_kernel (from log-mel) launch");
+  }
   float* mfcc = mfcc_out ? mfcc_out : (float*)carve(cur, (size_t)n_clips * c.n_mfcc * T * 4);
   if ((rc = mmf_mfcc(p, logmel, clipmax, n_clips, T, mfcc, delta_out, clamp_in_place, st))) return rc;
   // fused per-clip kernel: row filters, derivative + norm and the output filter with the
   // float64 rows resident in shared memory (script/mfcc.py:393-425)
-  SosPar pa, po;
-  size_t fsmem = 0;
-  const bool out_iir = prm->out_kind == 0;
-  if (!(c.flags & MMF_FLAG_UNFUSED_CHANGE) && sos_par_fill(sa, T, &pa) && (!out_iir || sos_par_fill(so, T, &po)) &&
-      change_fused_supported(pa, out_iir ? &po : nullptr, rows, T, &fsmem)) {
+  if (par_ok && change_fused_supported(pa, out_iir ? &po : nullptr, rows, T, &fsmem)) {
     cudaError_t e = change_fused_launch(mfcc, n_clips, c.n_mfcc, first, rows, T, prm->diff_method, pa,
-                                        out_iir ? po : pa, prm->out_kind, tot, fsmem, st);
+                                        out_iir ? po : pa, prm->out_kind, tot, fsmem, nullptr, st);
     if (e == cudaSuccess) return MMF_OK;
     if (e != cudaErrorNotSupported) return cuda_fail(e, "change_fused_kernel launch");
   }

@@ -9,6 +9,7 @@
 //    output filter of the resulting curve (script/mfcc.py:417-425) -- the
 //    float64 intermediates (96 KB per 10 s clip) never touch HBM.
 #include <algorithm>
+#include <cfloat>
 #include <cstring>
 #include <vector>
 
@@ -327,21 +328,117 @@ cudaError_t sosfiltfilt_long_launch(const void* x, int x_is_f32, long rows, long
 // ---------------------------------------------------------------------------
 // fused per-clip kernel
 // ---------------------------------------------------------------------------
-template <int NS1, int NS2>
+// K3 folded into the per-clip kernel: clamp + DCT-II of this clip's log-mel columns straight into the
+// float64 row buffers (and to HBM as float32 MFCC / delta when the caller wants them).  Same FMA order
+// per coefficient as mfcc_kernel (post_kernels.cu), so the MFCCs are bit-identical to the unfused path.
+constexpr int kFusedNC = 16;
+constexpr int kFusedDepth = 8;  // log-mel rows in flight per thread (16 measured slower)
+__device__ __forceinline__ float fused_key_to_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+
+__device__ __forceinline__ void fused_mfcc_phase(const FusedMfccArgs& m, long clip, int n_mfcc, int first, int T,
+                                                 int S, int p, double* rowbuf, float* s_dct) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+  const int n_mels = m.n_mels;
+  for (int i = tid; i < n_mels * kFusedNC; i += nthr) {
+    const int mm = i / kFusedNC, j = i - mm * kFusedNC;
+    s_dct[i] = m.dct_pad[mm * m.dct_pitch + j];
+  }
+  __syncthreads();
+  const float thr = m.top_db >= 0.0f ? fused_key_to_float(m.clipmax[clip]) - m.top_db : -FLT_MAX;
+  // a warp takes 32 consecutive frames; with delta wanted the outer two are a halo (recomputed by the
+  // neighbouring tile) so that t-1 / t+1 come from lane shuffles instead of shared memory
+  const int halo = m.delta_out != nullptr ? 1 : 0;
+  const int width = 32 - 2 * halo;
+  const int n_tiles = (T + width - 1) / width;
+  for (int tile = tid >> 5; tile < n_tiles; tile += nthr >> 5) {
+    const int t = tile * width - halo + lane;
+    const bool valid = t >= 0 && t < T;
+    const bool own = valid && lane >= halo && lane < 32 - halo;
+    float acc[kFusedNC];
+#pragma unroll
+    for (int j = 0; j < kFusedNC; ++j) acc[j] = 0.0f;
+    if (valid) {
+      float* col = m.logmel + (size_t)clip * n_mels * T + t;
+      float cur[kFusedDepth], nxt[kFusedDepth];
+#pragma unroll
+      for (int u = 0; u < kFusedDepth; ++u) cur[u] = (u < n_mels) ? __ldcs(col + (size_t)u * T) : 0.0f;
+      for (int m0 = 0; m0 < n_mels; m0 += kFusedDepth) {
+#pragma unroll
+        for (int u = 0; u < kFusedDepth; ++u)
+          nxt[u] = (m0 + kFusedDepth + u < n_mels) ? __ldcs(col + (size_t)(m0 + kFusedDepth + u) * T) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < kFusedDepth; ++u) {
+          const int mm = m0 + u;
+          if (mm < n_mels) {
+            const float x = fmaxf(cur[u], thr);
+            if (m.clamp_in_place && own) col[(size_t)mm * T] = x;
+            const float4* d4 = reinterpret_cast<const float4*>(s_dct + mm * kFusedNC);
+#pragma unroll
+            for (int j4 = 0; j4 < kFusedNC / 4; ++j4) {
+              const float4 d = d4[j4];
+              acc[4 * j4 + 0] = fmaf(d.x, x, acc[4 * j4 + 0]);
+              acc[4 * j4 + 1] = fmaf(d.y, x, acc[4 * j4 + 1]);
+              acc[4 * j4 + 2] = fmaf(d.z, x, acc[4 * j4 + 2]);
+              acc[4 * j4 + 3] = fmaf(d.w, x, acc[4 * j4 + 3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kFusedDepth; ++u) cur[u] = nxt[u];
+      }
+    }
+    if (own) {
+      float* dst = m.mfcc_out ? m.mfcc_out + (size_t)clip * n_mfcc * T + t : nullptr;
+#pragma unroll
+      for (int j = 0; j < kFusedNC; ++j) {
+        if (j < n_mfcc) {
+          if (dst) dst[(size_t)j * T] = acc[j];
+          if (j >= first) rowbuf[(size_t)(j - first) * S + p + t] = (double)acc[j];
+        }
+      }
+    }
+    if (halo) {
+      // delta = np.gradient along time in float32 (calc.py:642-645); shuffles stay outside any
+      // lane-dependent branch
+      float* dst = m.delta_out + (size_t)clip * n_mfcc * T + t;
+#pragma unroll
+      for (int j = 0; j < kFusedNC; ++j) {
+        if (j < n_mfcc) {
+          const float cp = __shfl_down_sync(0xffffffffu, acc[j], 1);
+          const float cm = __shfl_up_sync(0xffffffffu, acc[j], 1);
+          float d;
+          if (T == 1) d = 0.0f;
+          else if (t == 0) d = cp - acc[j];
+          else if (t == T - 1) d = acc[j] - cm;
+          else d = (cp - cm) / 2.0f;
+          if (own) dst[(size_t)j * T] = d;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <int NS1, int NS2, bool FROM_LM>
 __global__ void __launch_bounds__(kFusedMaxWarps * 32, 2)
     change_fused_kernel(const float* __restrict__ mfcc, int n_mfcc, int first, int rows, int T, int method,
                         const __grid_constant__ SosPar a1, const __grid_constant__ SosPar a2, int out_kind,
-                        double* __restrict__ tot) {
+                        double* __restrict__ tot, const __grid_constant__ FusedMfccArgs lm, int sm_doubles) {
   extern __shared__ __align__(16) double sm_fused[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const long clip = blockIdx.x;
   const int S = 32 * a1.CL, p = a1.padlen, L = T + 2 * p;
+  if (FROM_LM) {
+    float* s_dct = reinterpret_cast<float*>(sm_fused + sm_doubles);
+    fused_mfcc_phase(lm, clip, n_mfcc, first, T, S, p, sm_fused, s_dct);
+  }
   // 1. zero-phase Butterworth of every kept coefficient row, in place in shared memory
   {
     const SosRegs<NS1> c1(a1);
     for (int r = warp; r < rows; r += nwarps) {
       double* buf = sm_fused + (size_t)r * S;
-      warp_load_odd_ext<float>(mfcc + ((size_t)clip * n_mfcc + first + r) * T, T, p, buf, S, lane);
+      if (FROM_LM) warp_odd_ext_staged<float>(buf, T, p, S, lane);
+      else warp_load_odd_ext<float>(mfcc + ((size_t)clip * n_mfcc + first + r) * T, T, p, buf, S, lane);
       warp_sosfiltfilt<NS1>(buf, L, a1, c1, lane);
     }
   }
@@ -406,11 +503,26 @@ __global__ void __launch_bounds__(kFusedMaxWarps * 32, 2)
   for (int t = tid; t < T; t += blockDim.x) dst[t] = cbuf[p2 + t];
 }
 
-bool change_fused_supported(const SosPar& a1, const SosPar* a2, int rows, long T, size_t* smem_out) {
-  if (rows < 1 || T < 1 || T > (long)kFusedMaxWarps * 32 * kFusedPerThread) return false;
+static size_t fused_row_doubles(const SosPar& a1, const SosPar* a2, int rows) {
   size_t doubles = (size_t)rows * 32 * a1.CL;
   if (a2) doubles = std::max(doubles, (size_t)32 * a2->CL);
-  const size_t smem = doubles * sizeof(double);
+  return doubles;
+}
+
+bool change_fused_supported(const SosPar& a1, const SosPar* a2, int rows, long T, size_t* smem_out) {
+  if (rows < 1 || T < 1 || T > (long)kFusedMaxWarps * 32 * kFusedPerThread) return false;
+  const size_t smem = fused_row_doubles(a1, a2, rows) * sizeof(double);
+  if (smem > 220 * 1024) return false;
+  if (smem_out) *smem_out = smem;
+  return true;
+}
+
+// with the MFCC stage folded in: + the DCT table
+bool change_fused_lm_supported(const SosPar& a1, const SosPar* a2, int n_mfcc, int n_mels, int first, int rows,
+                               long T, size_t* smem_out) {
+  size_t base = 0;
+  if (n_mfcc > kFusedNC || !change_fused_supported(a1, a2, rows, T, &base)) return false;
+  const size_t smem = base + (size_t)n_mels * kFusedNC * sizeof(float);
   if (smem > 220 * 1024) return false;
   if (smem_out) *smem_out = smem;
   return true;
@@ -419,25 +531,37 @@ bool change_fused_supported(const SosPar& a1, const SosPar* a2, int rows, long T
 template <int NS1, int NS2>
 static cudaError_t fused_launch_cl(const float* mfcc, long n_clips, int n_mfcc, int first, int rows, long T,
                                    int method, const SosPar& a1, const SosPar& a2, int out_kind, double* tot,
-                                   size_t smem, cudaStream_t st) {
+                                   size_t smem, const FusedMfccArgs* lm, cudaStream_t st) {
   // >= ceil(T / (32*kFusedPerThread)) warps for the derivative phase, one per row if possible
-  const int warps = std::min(kFusedMaxWarps, std::max(rows, (int)((T + 32 * kFusedPerThread - 1) / (32 * kFusedPerThread))));
-  auto kfn = change_fused_kernel<NS1, NS2>;
-  MMF_SMEM_ONCE(kfn, 220 * 1024);
-  kfn<<<(unsigned)n_clips, warps * 32, smem, st>>>(mfcc, n_mfcc, first, rows, (int)T, method, a1, a2, out_kind, tot);
+  int warps = std::min(kFusedMaxWarps, std::max(rows, (int)((T + 32 * kFusedPerThread - 1) / (32 * kFusedPerThread))));
+  const int sm_doubles = (int)fused_row_doubles(a1, out_kind == 0 ? &a2 : nullptr, rows);
+  if (lm) {
+    // the DCT phase streams the clip's log-mel columns: it wants every thread the CTA may have
+    warps = kFusedMaxWarps;
+    auto kfn = change_fused_kernel<NS1, NS2, true>;
+    MMF_SMEM_ONCE(kfn, 220 * 1024);
+    kfn<<<(unsigned)n_clips, warps * 32, smem, st>>>(nullptr, n_mfcc, first, rows, (int)T, method, a1, a2, out_kind,
+                                                     tot, *lm, sm_doubles);
+  } else {
+    auto kfn = change_fused_kernel<NS1, NS2, false>;
+    MMF_SMEM_ONCE(kfn, 220 * 1024);
+    kfn<<<(unsigned)n_clips, warps * 32, smem, st>>>(mfcc, n_mfcc, first, rows, (int)T, method, a1, a2, out_kind,
+                                                     tot, FusedMfccArgs{}, sm_doubles);
+  }
   count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t change_fused_launch(const float* mfcc, long n_clips, int n_mfcc, int first, int rows, long T, int method,
                                 const SosPar& a1, const SosPar& a2, int out_kind, double* tot, size_t smem,
-                                cudaStream_t st) {
+                                const FusedMfccArgs* lm, cudaStream_t st) {
   // equal section counts (the reference's default: outFilter None reuses the row filter, 'iir' uses
   // the same order) get an instantiation; anything else goes through the unfused kernels
   const int k = a1.ns * 10 + (out_kind == 0 ? a2.ns : a1.ns);
   switch (k) {
 #define MMF_FUSED_CASE(A, B) \
-  case A * 10 + B: return fused_launch_cl<A, B>(mfcc, n_clips, n_mfcc, first, rows, T, method, a1, a2, out_kind, tot, smem, st);
+  case A * 10 + B:           \
+    return fused_launch_cl<A, B>(mfcc, n_clips, n_mfcc, first, rows, T, method, a1, a2, out_kind, tot, smem, lm, st);
     MMF_FUSED_CASE(1, 1)
     MMF_FUSED_CASE(2, 2)
     MMF_FUSED_CASE(3, 3)

@@ -102,9 +102,24 @@ bool sos_long_supported(const SosArgs& a, long rows, long T);
 cudaError_t sosfiltfilt_long_launch(const void* x, int x_is_f32, long rows, long T, long xs, int group_rows,
                                     long group_stride, const SosArgs& a, double* y, long ys, cudaStream_t st);
 bool change_fused_supported(const SosPar& a1, const SosPar* a2, int rows, long T, size_t* smem_out);
+// K3 folded into the fused kernel (lm != nullptr): the clip's MFCC rows go from the DCT straight into
+// the float64 row buffers; mfcc_out / delta_out are optional HBM copies for the caller
+struct FusedMfccArgs {
+  const float* dct_pad;
+  int dct_pitch;
+  float* logmel;
+  const int* clipmax;
+  int n_mels;
+  float top_db;
+  float* mfcc_out;
+  float* delta_out;
+  int clamp_in_place;
+};
+bool change_fused_lm_supported(const SosPar& a1, const SosPar* a2, int n_mfcc, int n_mels, int first, int rows,
+                               long T, size_t* smem_out);
 cudaError_t change_fused_launch(const float* mfcc, long n_clips, int n_mfcc, int first, int rows, long T, int method,
                                 const SosPar& a1, const SosPar& a2, int out_kind, double* tot, size_t smem,
-                                cudaStream_t st);
+                                const FusedMfccArgs* lm, cudaStream_t st);
 cudaError_t delta_norm_launch(const double* x, long n_clips, int rows, long T, int method, double* tot,
                               cudaStream_t st);
 cudaError_t fir_filtfilt_launch(const double* x, long rows, long T, const double* b_dev, int n_taps, double* y,

@@ -144,14 +144,10 @@ __device__ __forceinline__ void warp_sosfiltfilt(double* buf, int L, const SosPa
 // odd extension (scipy.signal._arraytools.odd_ext) of row x[0..T) into buf[0..T+2p),
 // computed in the input dtype as scipy does, then widened; buf[L..S) is zeroed.
 template <typename TIn>
-__device__ __forceinline__ void warp_load_odd_ext(const TIn* __restrict__ x, int T, int p, double* buf, int S,
-                                                  int lane) {
+__device__ __forceinline__ void warp_odd_ext_staged(double* buf, int T, int p, int S, int lane) {
+  // both extensions from the staged interior buf[p .. p+T) (values are exactly representable in TIn);
+  // scipy's odd_ext does this arithmetic in the input dtype
   const int L = T + 2 * p;
-  // interior: plain coalesced stream (unrolled so that several loads are in flight)
-#pragma unroll 8
-  for (int t = lane; t < T; t += 32) buf[p + t] = (double)x[t];
-  __syncwarp();
-  // both extensions from the staged interior (values are exactly representable in TIn)
   const TIn two = (TIn)2;
   const TIn x0 = (TIn)buf[p], xl = (TIn)buf[p + T - 1];
   for (int i = lane; i < p; i += 32) {
@@ -160,6 +156,16 @@ __device__ __forceinline__ void warp_load_odd_ext(const TIn* __restrict__ x, int
   }
   for (int i = L + lane; i < S; i += 32) buf[i] = 0.0;
   __syncwarp();
+}
+
+template <typename TIn>
+__device__ __forceinline__ void warp_load_odd_ext(const TIn* __restrict__ x, int T, int p, double* buf, int S,
+                                                  int lane) {
+  // interior: plain coalesced stream (unrolled so that several loads are in flight)
+#pragma unroll 8
+  for (int t = lane; t < T; t += 32) buf[p + t] = (double)x[t];
+  __syncwarp();
+  warp_odd_ext_staged<TIn>(buf, T, p, S, lane);
 }
 
 }  // namespace mmf

@@ -246,6 +246,35 @@ def test_fused_change_kernel_equals_unfused(cuda_device):
             assert np.max(np.abs(fused[i] - ref)) < ABS_TOL, over
 
 
+@pytest.mark.parametrize("name", ["cfg1_16k", "gui_default", "n256"])
+@pytest.mark.parametrize("remove_first,clamp", [(1, True), (0, False)])
+def test_per_clip_kernel_from_logmel_is_bit_identical(name, remove_first, clamp, cuda_device):
+    """The per-clip kernel with clamp + DCT-II folded in (MMF_FLAG_FOLD_MFCC; the default when no
+    delta is requested) against the separate MFCC kernel followed by the per-clip kernel
+    (MMF_FLAG_SEPARATE_MFCC): same FMA order, so MFCC, delta, the clamped log-mel written back
+    and the curve must be bit-identical."""
+    cfg, secs = _cfg(name)
+    y = synth_batch(77, 3, int(cfg.sample_rate * max(secs, 1.0)), cfg.sample_rate)
+    sos = scipy.signal.butter(6, 12.0, "low", fs=cfg.sample_rate / cfg.hop_length, output="sos")
+    prm = mm.plan.make_change_params(sos, remove_first=remove_first, diff_method=0, out_sos=sos)
+    res = []
+    for flags in (_lib.MMF_FLAG_FOLD_MFCC, _lib.MMF_FLAG_SEPARATE_MFCC):
+        plan = mm.get_plan(mm.plan.replace(cfg, flags=flags))
+        lm, cmax = plan.logmel(y)
+        out = plan.change_from_logmel(lm, cmax, prm, want_delta=True, clamp_in_place=clamp)
+        res.append({k: v.cpu().numpy() for k, v in out.items()} | {"logmel": lm.cpu().numpy()})
+        # no delta requested: the default folds (one launch fewer than with the separate kernel)
+        lm2, cmax2 = plan.logmel(y)
+        n0 = _lib.lib().mmf_launch_count(0)
+        out2 = plan.change_from_logmel(lm2, cmax2, prm, want_delta=False, clamp_in_place=clamp)
+        res[-1]["launches"] = _lib.lib().mmf_launch_count(0) - n0
+        assert np.array_equal(out2["totChange"].cpu().numpy(), res[-1]["totChange"])
+        assert np.array_equal(out2["mfcc"].cpu().numpy(), res[-1]["mfcc"])
+    for k in ("logmel", "mfcc", "delta", "totChange"):
+        assert np.array_equal(res[0][k], res[1][k]), (name, k)
+    assert (res[0]["launches"], res[1]["launches"]) == (1, 2)
+
+
 KW_GUI = dict(channelN=0, tStep=0.005, winLen=0.025, n_mfcc=13, n_fft=512, minFreq=100, maxFreq=10000, removeFirst=1,
               filtCutoff=12, filtOrd=6, diffMethod="grad", outFilter="iir", outFiltType="low", outFiltCutOff=[12],
               outFiltLen=6, outFiltPolyOrd=3)
