@@ -87,7 +87,9 @@ __host__ __device__ inline int tile_index(int r, int k, int K) {
 
 // a_in_tmem is a template parameter: the issuing thread's loop must stay free of branches and of
 // descriptor arithmetic (UTCHMMA takes uniform registers; a runtime switch here doubled the issue time)
-template <bool a_in_tmem>
+// two_issuers: lane 0 of warp 1 issues the same stream into a second accumulator -- tells whether the
+// ~45-cycle floor per small MMA is the issuing thread or the tensor pipe
+template <bool a_in_tmem, bool two_issuers = false>
 __global__ void __launch_bounds__(128)
     tf32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int iters,
                 long long* __restrict__ cycles, int* __restrict__ err) {
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(128)
   float* sA = reinterpret_cast<float*>(smem);                 // 128 x 32 floats = 16 KB
   float* sB = sA + kM * kK;                                   // N x 32 floats
   __shared__ __align__(8) unsigned long long bar;
+  __shared__ __align__(8) unsigned long long bar2;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(128)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   int ncols = 32;
-  while (ncols < N + (a_in_tmem ? kK : 0)) ncols <<= 1;
+  while (ncols < N + (a_in_tmem ? kK : 0) + (two_issuers ? N : 0)) ncols <<= 1;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(ncols)
                  : "memory");
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(128)
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -157,6 +161,23 @@ __global__ void __launch_bounds__(128)
     const long long t1 = clock64();
     if (!ok) atomicExch(err, 1);
     cycles[blockIdx.x] = t1 - t0;
+  }
+  if (two_issuers && tid == 32) {
+    const uint32_t lbo = 128, sbo = (kK / 4) * 128;
+    const uint64_t adesc0 = make_desc(smem_u32(sA), lbo, sbo);
+    const uint64_t bdesc0 = make_desc(smem_u32(sB), lbo, sbo);
+    const uint32_t idesc = make_idesc(kM, N);
+    const uint32_t d2 = taddr + (uint32_t)(N + (a_in_tmem ? kK : 0));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int s = 0; s < kK / 8; ++s) {
+        if (a_in_tmem) mma_tf32_ts(d2, a_tmem + (uint32_t)(s * 8), bdesc0 + (uint64_t)(s * 16), idesc, (it | s) ? 1u : 0u);
+        else mma_tf32(d2, adesc0 + (uint64_t)(s * 16), bdesc0 + (uint64_t)(s * 16), idesc, (it | s) ? 1u : 0u);
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2))
+                 : "memory");
+    if (!mbar_wait(smem_u32(&bar2), 0)) atomicExch(err, 1);
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -239,13 +260,16 @@ int main() {
   cudaMemset(dErr, 0, 4);
   cudaFuncSetAttribute(tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  for (int mode = 0; mode < 2; ++mode)
+  cudaFuncSetAttribute(tf32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int mode = 0; mode < 3; ++mode)
   for (int N : {32, 64, 128, 256}) {
-    const char* tag = mode ? "A in TMEM" : "A in smem";
+    if (mode == 2 && N > 128) continue;
+    const char* tag = mode == 2 ? "A in smem, 2 issuers" : mode ? "A in TMEM" : "A in smem";
     const size_t smem = (size_t)(kM + N) * kK * 4;
     // known answer: one pass
     cudaMemset(dD, 0, kM * 256 * 4);
-    if (mode) tf32_kernel<true><<<1, 128, smem>>>(dA, dB, dD, N, 1, dC, dErr);
+    if (mode == 2) tf32_kernel<false, true><<<1, 128, smem>>>(dA, dB, dD, N, 1, dC, dErr);
+    else if (mode) tf32_kernel<true><<<1, 128, smem>>>(dA, dB, dD, N, 1, dC, dErr);
     else tf32_kernel<false><<<1, 128, smem>>>(dA, dB, dD, N, 1, dC, dErr);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -269,7 +293,8 @@ int main() {
     if (herr || !(worst < 1e-5)) continue;
     // rate: every SM issuing
     const int iters = 4000;
-    if (mode) tf32_kernel<true><<<nsm, 128, smem>>>(dA, dB, dD, N, iters, dC, dErr);
+    if (mode == 2) tf32_kernel<false, true><<<nsm, 128, smem>>>(dA, dB, dD, N, iters, dC, dErr);
+    else if (mode) tf32_kernel<true><<<nsm, 128, smem>>>(dA, dB, dD, N, iters, dC, dErr);
     else tf32_kernel<false><<<nsm, 128, smem>>>(dA, dB, dD, N, iters, dC, dErr);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -287,7 +312,7 @@ int main() {
     cyc /= nsm;
     rd /= nsm;
     rd32 /= nsm;
-    const double per_mma = cyc / (iters * (kK / 8));
+    const double per_mma = cyc / (iters * (kK / 8)) / (mode == 2 ? 2 : 1);
     const double flop_per_mma = 2.0 * kM * N * 8;
     std::printf("%s N %3d: %.1f cycles per MMA (m128 n%d k8) = %.0f flop/clk/SM = %.0f TFLOP/s at %.0f MHz on %d SMs; "
                 "read-back of 128 x %d fp32 by 4 warps: %.0f cycles (x32 loads), %.0f (x8 loads + stores)\n",
