@@ -6,7 +6,9 @@ A 512-point real frame = 256-point complex FFT of the packed samples = two radix
 split (x = hi + lo [+ lo2]) and the product rebuilt from several MMAs.  This script emulates that on the
 host (TF32 operands = fp32 with the low 13 mantissa bits dropped, products exact, fp32 accumulation) and
 reports the error of the linear mel power per band against float64, next to a plain fp32 FFT -- the
-quantity the parity tests bound by 1e-4 (tests/test_gpu_parity.py LOGMEL_REL).
+quantity the parity tests bound by 1e-4 (tests/test_gpu_parity.py LOGMEL_REL).  `kind::f16` runs at twice the
+TF32 rate with the same 11-bit significand; its 5-bit exponent needs a power-of-two scale per frame and the
+low parts carried at 2^11 in their own accumulator ("fp16 x3").
 
     python tools/tf32_dft_study.py            # CPU only, a few seconds
 """
@@ -44,6 +46,58 @@ def mma(a_terms, b_terms, pairs):
         for k0 in range(0, K, 8):
             acc = (acc + (a[:, k0:k0 + 8] @ b[k0:k0 + 8, :]).astype(np.float32)).astype(np.float32)
     return acc
+
+
+def split_f16(x, scale):
+    """x (fp32) -> fp16 pair (hi, lo) with x ~= (hi + lo * 2^-11) / scale; values as fp32 arrays."""
+    xs = (np.asarray(x, dtype=np.float32) * np.float32(scale)).astype(np.float32)
+    hi = xs.astype(np.float16).astype(np.float32)
+    lo = ((xs - hi) * np.float32(2048.0)).astype(np.float16).astype(np.float32)
+    return hi, lo
+
+
+def mma_f16x3(a, b_hi, b_lo, row_scale):
+    """fp16 x3: acc0 = hi.F_hi, acc1 = hi.F_lo + lo.F_hi (both carry 2^-11), K = 16 slabs, fp32 accumulate."""
+    hi, lo = split_f16(a, 1.0)  # caller pre-scales rows
+    acc0 = np.zeros((a.shape[0], b_hi.shape[1]), dtype=np.float32)
+    acc1 = np.zeros_like(acc0)
+    for k0 in range(0, a.shape[1], 16):
+        sl = slice(k0, k0 + 16)
+        acc0 = (acc0 + (hi[:, sl].astype(np.float64) @ b_hi[sl].astype(np.float64)).astype(np.float32)).astype(np.float32)
+        acc1 = (acc1 + (hi[:, sl].astype(np.float64) @ b_lo[sl].astype(np.float64)).astype(np.float32)).astype(np.float32)
+        acc1 = (acc1 + (lo[:, sl].astype(np.float64) @ b_hi[sl].astype(np.float64)).astype(np.float32)).astype(np.float32)
+    return ((acc0 + acc1 * np.float32(2.0 ** -11)) / row_scale).astype(np.float32)
+
+
+def fft256_two_stage_f16(z):
+    """Same two GEMM stages with fp16 operands: every 8-frame row block is scaled by a power of two so that
+    its largest |value| sits near 2^6 (stage outputs grow 16x per stage and must stay below 65504)."""
+    F16 = np.exp(-2j * np.pi * np.outer(np.arange(16), np.arange(16)) / 16)
+    R = real_rep(F16).astype(np.float32)
+    b_hi, b_lo = split_f16(R, 1.0)
+    nf = z.shape[0]
+
+    def stage(a_ri):
+        rows = a_ri.reshape(nf, -1)
+        mx = np.maximum(np.abs(rows).max(axis=1), 1e-30)
+        sc = np.exp2(6 - np.ceil(np.log2(mx))).astype(np.float32)  # per frame, power of two
+        sc_rows = np.repeat(sc, 16)[:, None]
+        return mma_f16x3((a_ri * sc_rows).astype(np.float32), b_hi, b_lo, sc_rows)
+
+    x = z.reshape(nf, 16, 16)
+    a = np.transpose(x, (0, 2, 1)).reshape(nf * 16, 16)
+    a_ri = np.empty((nf * 16, 32), dtype=np.float32)
+    a_ri[:, 0::2], a_ri[:, 1::2] = a.real, a.imag
+    d1 = stage(a_ri)
+    y = (d1[:, 0::2] + 1j * d1[:, 1::2]).astype(np.complex64).reshape(nf, 16, 16)
+    tw = np.exp(-2j * np.pi * np.outer(np.arange(16), np.arange(16)) / 256).astype(np.complex64)
+    y = (y * tw[None]).astype(np.complex64)
+    a2 = np.transpose(y, (0, 2, 1)).reshape(nf * 16, 16)
+    a2_ri = np.empty((nf * 16, 32), dtype=np.float32)
+    a2_ri[:, 0::2], a2_ri[:, 1::2] = a2.real, a2.imag
+    d2 = stage(a2_ri)
+    Z = (d2[:, 0::2] + 1j * d2[:, 1::2]).reshape(nf, 16, 16)
+    return np.transpose(Z, (0, 2, 1)).reshape(nf, 256)
 
 
 def real_rep(F):
@@ -125,6 +179,7 @@ def main():
     report("fp32 FFT", np.abs(scipy.fft.rfft(fr, axis=1).astype(np.complex128)) ** 2)
     for scheme in PAIRS:
         report(scheme, power_from_packed(fft256_two_stage(z, scheme)))
+    report("fp16 x3", power_from_packed(fft256_two_stage_f16(z)))
 
 
 if __name__ == "__main__":
