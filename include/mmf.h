@@ -64,6 +64,8 @@ typedef struct {
 #define MMF_FLAG_MMA_DCT 32       /* clamp + DCT-II on the tensor cores (mma.sync TF32 x3) instead of scalar FP32 FMAs */
 #define MMF_FLAG_UNFUSED_CHANGE 4 /* composite calls: separate filter / derivative kernels instead of the fused one */
 #define MMF_FLAG_SEPARATE_MFCC 64 /* composite calls: clamp + DCT-II always as its own kernel */
+#define MMF_FLAG_TC_FFT 256       /* n_fft = 512: the transform as tcgen05.mma kind::f16 GEMMs (fp16 x3 operand split,
+                                     accumulators in tensor memory); mmf_stft_power only so far */
 #define MMF_FLAG_FOLD_MFCC 128    /* composite calls: clamp + DCT-II inside the per-clip kernel even when delta is wanted
                                      (default: folded only when no delta output is requested; measured in DESIGN.md) */
 

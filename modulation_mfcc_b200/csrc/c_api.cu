@@ -491,6 +491,21 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     return cuda_fail(e, "uploading plan constants");
   }
 
+  if ((cfg->flags & MMF_FLAG_TC_FFT) && tc_fft_supported(cfg->n_fft, cfg->hop_length, cfg->preemph)) {
+    std::vector<uint16_t> btab;
+    std::vector<float> twf;
+    tc_fft_tables(btab, twf);
+    uint16_t* d_b = nullptr;
+    float* d_t = nullptr;
+    if ((e = upload(&d_b, btab)) != cudaSuccess || (e = upload(&d_t, twf)) != cudaSuccess) {
+      cudaFree(d_b);
+      mmf_plan_destroy(p);
+      return cuda_fail(e, "uploading tensor-core transform tables");
+    }
+    p->d_tc_btab = d_b;
+    p->d_tc_tw = reinterpret_cast<float2*>(d_t);
+  }
+
   // ---- driver entry point for tensor-map encoding (no link-time libcuda dependency)
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -507,6 +522,8 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaSetDevice(p->cfg.device);
   cudaDeviceSynchronize();
   cudaFree(p->d_window);
+  cudaFree(p->d_tc_btab);
+  cudaFree(p->d_tc_tw);
   cudaFree(p->d_tw1);
   cudaFree(p->d_tw2);
   cudaFree(p->d_seg);
@@ -649,6 +666,18 @@ extern "C" {
 int mmf_stft_power(mmf_plan* plan, const float* pcm_dev, int64_t n_clips, int64_t n_samples, int64_t clip_stride,
                    float* power_dev, void* stream) {
   if (!power_dev) return fail(MMF_ERR_INVALID, "power_dev is NULL");
+  if (plan && plan->d_tc_btab && pcm_dev && n_clips >= 1 && n_samples >= 1 && (clip_stride >= n_samples || n_clips == 1)) {
+    // tcgen05 transform (MMF_FLAG_TC_FFT): fp16 x3 GEMM stages, accumulators in tensor memory
+    const int64_t T = mmf_num_frames(n_samples, plan->cfg.n_fft, plan->cfg.hop_length);
+    if (T >= 1 && T <= 0x7fffffff) {
+      MMF_CUDA(cudaSetDevice(plan->cfg.device));
+      cudaError_t e = tc_fft_power_launch(pcm_dev, n_clips, n_samples, clip_stride, (int)T, plan->cfg.hop_length,
+                                          plan->d_window, plan->d_tc_btab, plan->d_tc_tw, power_dev, plan->sm_count,
+                                          (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_fail(e, "tc_fft512_kernel launch");
+      return MMF_OK;
+    }
+  }
   return run_stft(plan, pcm_dev, n_clips, n_samples, clip_stride, power_dev, nullptr, nullptr, (cudaStream_t)stream);
 }
 

@@ -72,6 +72,13 @@ size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
                             cudaStream_t st);
 
+// ---- 512-point frames on the tcgen05 tensor cores (tc_fft.cu, MMF_FLAG_TC_FFT)
+void tc_fft_tables(std::vector<uint16_t>& btab, std::vector<float>& tw);
+bool tc_fft_supported(int n_fft, int hop, float preemph);
+cudaError_t tc_fft_power_launch(const float* pcm, long n_clips, long n_samples, long clip_stride, int T, int hop,
+                                const float* window, const void* btab, const float2* tw, float* power, int sm_count,
+                                cudaStream_t st);
+
 // ---- post-FFT kernels (post_kernels.cu)
 cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const int* clipmax, long n_clips, long T,
                         int n_mels, int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place,
@@ -204,6 +211,8 @@ struct mmf_plan {
   float4* d_dct_bfrag = nullptr;  // DCT B fragments of the tensor-core MFCC kernel
   int nc_pad = 0;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  void* d_tc_btab = nullptr;    // fp16 DFT operand tables of the tensor-core transform (MMF_FLAG_TC_FFT)
+  float2* d_tc_tw = nullptr;
   // tables of the trajectory FFT, rebuilt when (win, nfft, bands) change
   int mod_win = 0, mod_nfft = 0, mod_n_bands = -1;
   int mod_lo[16] = {0}, mod_hi[16] = {0};

@@ -77,6 +77,27 @@ def test_stft_power(name, flags, cuda_device):
         assert np.max(np.abs(P[i] - ref) / peak) < 2e-6, name
 
 
+@pytest.mark.parametrize("name", ["cfg1_16k", "gui_default"])
+def test_stft_power_tensor_core_transform(name, cuda_device):
+    """MMF_FLAG_TC_FFT: the 512-point transform as tcgen05.mma kind::f16 GEMM stages (fp16 x3 operand
+    split, accumulators in tensor memory) against the oracle, same bound as the FP32 kernel, and
+    against the FP32 kernel itself; ragged frame counts, a silent clip and a loud one included."""
+    cfg, secs = _cfg(name, flags=_lib.MMF_FLAG_TC_FFT)
+    n = int(cfg.sample_rate * secs) + 37
+    y = synth_batch(0, 5, n, cfg.sample_rate)
+    y[3] = 0.0
+    y[4] *= 1000.0
+    P = mm.get_plan(cfg).stft_power(y).cpu().numpy()
+    Q = mm.get_plan(mm.plan.replace(cfg, flags=0)).stft_power(y).cpu().numpy()
+    assert P.shape == Q.shape
+    assert np.all(P[3] == 0.0)
+    for i in (0, 1, 2, 4):
+        ref = oracle.stft_power(y[i], cfg.n_fft, cfg.hop_length, cfg.win_length)
+        peak = ref.max(axis=0, keepdims=True)
+        assert np.max(np.abs(P[i] - ref) / peak) < 2e-6, (name, i)
+        assert np.max(np.abs(P[i] - Q[i]) / peak) < 2e-6, (name, i)
+
+
 def test_stft_power_split_variants_agree(cuda_device):
     cfg, secs = _cfg("cfg1_16k")
     y = synth_batch(5, 2, 16000 * 2, 16000)
