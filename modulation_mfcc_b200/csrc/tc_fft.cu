@@ -130,7 +130,7 @@ struct TcFftArgs {
 
 __global__ void __launch_bounds__(kTcThreads) tc_fft512_kernel(const TcFftArgs p) {
   extern __shared__ __align__(1024) unsigned char sm_tc[];
-  // carve (bytes): B tables 6144 | A1 hi 8192 | A1 lo 8192 | A2 hi 9216 | A2 lo 9216 | window 2048 | tw 2048 | span
+  // carve (bytes): B tables 6144 | A1 hi 8192 | A1 lo 8192 | A2 hi 9216 | A2 lo 9216 | window 2048 | tw 2048 | W512 2064 | span
   __half* sB64 = reinterpret_cast<__half*>(sm_tc);
   __half* sB32 = sB64 + 64 * 32;
   unsigned char* sA1h = sm_tc + 6144;
@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(kTcThreads) tc_fft512_kernel(const TcFftArgs p
   unsigned char* sA2l = sA2h + 16 * kA2Sbo;
   float* s_win = reinterpret_cast<float*>(sA2l + 16 * kA2Sbo);
   float2* s_tw = reinterpret_cast<float2*>(s_win + 512);
-  float* s_span = reinterpret_cast<float*>(s_tw + 256);
+  float2* s_w512 = s_tw + 256;  // [257] (cos, sin)(pi k / 256), 8-byte padded to 258
+  float* s_span = reinterpret_cast<float*>(s_w512 + 258);
   // the transformed frames reuse the stage-1 operand area: 8 x 257 complex = 16448 bytes > 16384, so they
   // start at A1 and run 64 bytes into A2 hi, which is dead by then (stage 2 has completed)
   float2* sZ = reinterpret_cast<float2*>(sA1h);
@@ -151,6 +152,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_fft512_kernel(const TcFftArgs p
     reinterpret_cast<uint4*>(sB64)[i] = reinterpret_cast<const uint4*>(p.btab)[i];
   for (int i = tid; i < 512; i += kTcThreads) s_win[i] = p.window[i];
   for (int i = tid; i < 256; i += kTcThreads) s_tw[i] = p.tw[i];
+  for (int i = tid; i < 257; i += kTcThreads) {
+    float sn, cs;
+    sincospif((float)i * (1.0f / 256.0f), &sn, &cs);
+    s_w512[i] = make_float2(cs, sn);
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(128)
                  : "memory");
@@ -179,8 +185,12 @@ __global__ void __launch_bounds__(kTcThreads) tc_fft512_kernel(const TcFftArgs p
   const uint32_t i64k = make_idesc(64, false), i32k = make_idesc(32, false);
   const uint32_t i64m = make_idesc(64, true), i32m = make_idesc(32, true);
 
+  const bool vec_ok = (p.hop & 1) == 0;
   const int f = tid >> 4, n1 = tid & 15;  // stage 1: row = (frame, n1); stage 2: row = (frame, k2 = n1)
   const int span_len = (kFB - 1) * p.hop + 512;
+  float2 wreg[16];  // window at the thread's own positions 2 (n1 + 16 n2), +1
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) wreg[n2] = *reinterpret_cast<const float2*>(s_win + 2 * (n1 + 16 * n2));
 
   for (long blk = blockIdx.x; blk < p.n_blocks; blk += gridDim.x) {
     const long clip = blk / p.blocks_per_clip;
@@ -204,8 +214,11 @@ __global__ void __launch_bounds__(kTcThreads) tc_fft512_kernel(const TcFftArgs p
 #pragma unroll
       for (int n2 = 0; n2 < 16; ++n2) {
         const int n = 2 * (n1 + 16 * n2);
-        v[2 * n2] = x[n] * s_win[n];
-        v[2 * n2 + 1] = x[n + 1] * s_win[n + 1];
+        float2 xv;
+        if (vec_ok) xv = *reinterpret_cast<const float2*>(x + n);  // (3) hop even: 8-byte aligned
+        else xv = make_float2(x[n], x[n + 1]);
+        v[2 * n2] = xv.x * wreg[n2].x;
+        v[2 * n2 + 1] = xv.y * wreg[n2].y;
         m = fmaxf(m, fmaxf(fabsf(v[2 * n2]), fabsf(v[2 * n2 + 1])));
       }
 #pragma unroll
@@ -317,8 +330,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_fft512_kernel(const TcFftArgs p
         // X[k] = (Z[k] + conj Z[256-k]) / 2 - i W512^k (Z[k] - conj Z[256-k]) / 2
         const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
         const float orr = 0.5f * (a.x - b.x), oi = 0.5f * (a.y + b.y);
-        float sn, cs;
-        sincospif((float)k * (1.0f / 256.0f), &sn, &cs);  // W512^k = cs - i sn
+        const float cs = s_w512[k].x, sn = s_w512[k].y;  // W512^k = cs - i sn
         // -i W (o) with o = orr + i oi:  W o = (cs orr + sn oi) + i (cs oi - sn orr);  -i (x + i y) = y - i x
         const float wr = cs * orr + sn * oi, wi = cs * oi - sn * orr;
         const float xr = er + wi, xi = ei - wr;
@@ -394,7 +406,7 @@ cudaError_t tc_fft_power_launch(const float* pcm, long n_clips, long n_samples, 
   a.btab = reinterpret_cast<const __half*>(btab);
   a.tw = tw;
   a.power = power;
-  const size_t smem = 6144 + 2 * 8192 + 2 * 16 * kA2Sbo + 2048 + 2048 + (size_t)((kFB - 1) * hop + 512) * 4;
+  const size_t smem = 6144 + 2 * 8192 + 2 * 16 * kA2Sbo + 2048 + 2048 + 258 * 8 + (size_t)((kFB - 1) * hop + 512) * 4;
   MMF_SMEM_ONCE(tc_fft512_kernel, 100 * 1024);
   // four CTAs per SM: 128 of the 512 TMEM columns and ~52 KB of shared memory each
   const long grid = std::min<long>(a.n_blocks, (long)sm_count * 4);
