@@ -111,6 +111,9 @@ static int ensure_mod_tables(mmf_plan* p, int win, int nfft, const int* lo, cons
   cudaFree(p->d_mod_tw2);
   cudaFree(p->d_mod_lo);
   cudaFree(p->d_mod_hi);
+  cudaFree(p->d_mod_g);
+  p->d_mod_g = nullptr;
+  p->mod_g_kp = 0;
   p->d_mod_hann = nullptr;
   p->d_mod_tw1 = p->d_mod_tw2 = nullptr;
   p->d_mod_lo = p->d_mod_hi = nullptr;
@@ -131,6 +134,13 @@ static int ensure_mod_tables(mmf_plan* p, int win, int nfft, const int* lo, cons
       (e = upload(&p->d_mod_tw2, tw2)) != cudaSuccess || (e = upload(&p->d_mod_lo, vlo)) != cudaSuccess ||
       (e = upload(&p->d_mod_hi, vhi)) != cudaSuccess)
     return cuda_fail(e, "uploading modulation-spectrum tables");
+  if (modspec_tc_supported(win, nfft) && (p->cfg.flags & MMF_FLAG_TC_MODSPEC)) {
+    std::vector<uint16_t> g;
+    uint16_t* d_g = nullptr;
+    modspec_tc_table(win, nfft, g, &p->mod_g_kp);
+    if ((e = upload(&d_g, g)) != cudaSuccess) return cuda_fail(e, "uploading modulation-spectrum GEMM operand");
+    p->d_mod_g = d_g;
+  }
   p->mod_win = win;
   p->mod_nfft = nfft;
   p->mod_n_bands = n_bands;
@@ -148,6 +158,14 @@ static int run_modspec(mmf_plan* p, const float* mfcc, int64_t n_clips, int n_co
   int rc = ensure_mod_tables(p, win, nfft, lo, hi, n_bands);
   if (rc) return rc;
   cudaError_t e;
+  if (p->d_mod_g != nullptr) {
+    // windowed DFT of 128 trajectory windows at a time as one tcgen05 GEMM (modspec_tc.cu)
+    bool handled = false;
+    e = modspec_tc_launch(mfcc, n_clips, n_coef, T, win, hop, nfft, p->d_mod_g, p->mod_g_kp, mag,
+                          n_bands > 0 ? band : nullptr, p->d_mod_lo, p->d_mod_hi, n_bands, p->sm_count, st, &handled);
+    if (e != cudaSuccess) return cuda_fail(e, "modspec_tc_kernel launch");
+    if (handled) return MMF_OK;
+  }
   if (modspec_fast_supported(nfft)) {
     e = modspec_fast_launch(mfcc, n_clips, n_coef, T, win, hop, nfft, p->d_mod_hann, p->d_mod_tw1, p->d_mod_tw2, mag,
                             n_bands > 0 ? band : nullptr, p->d_mod_lo, p->d_mod_hi, n_bands, p->sm_count, st);
@@ -542,6 +560,7 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_mod_tw2);
   cudaFree(p->d_mod_lo);
   cudaFree(p->d_mod_hi);
+  cudaFree(p->d_mod_g);
   if (p->pinned) cudaFreeHost(p->pinned);
   for (int i = 0; i < 2; ++i)
     if (p->streams[i]) cudaStreamDestroy(p->streams[i]);

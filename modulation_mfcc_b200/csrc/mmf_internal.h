@@ -79,6 +79,13 @@ cudaError_t tc_fft_power_launch(const float* pcm, long n_clips, long n_samples, 
                                 const float* window, const void* btab, const float2* tw, float* power, int sm_count,
                                 cudaStream_t st);
 
+// ---- modulation spectrum as a tcgen05 GEMM (modspec_tc.cu)
+bool modspec_tc_supported(int win, int nfft);
+void modspec_tc_table(int win, int nfft, std::vector<uint16_t>& g, int* kp_out);
+cudaError_t modspec_tc_launch(const float* mfcc, long n_clips, int n_coef, long T, int win, int hop, int nfft,
+                              const void* g, int kp, float* mag, float* band, const int* lo, const int* hi,
+                              int n_bands, int sm_count, cudaStream_t st, bool* handled);
+
 // ---- post-FFT kernels (post_kernels.cu)
 cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const int* clipmax, long n_clips, long T,
                         int n_mels, int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place,
@@ -221,6 +228,8 @@ struct mmf_plan {
   float2* d_mod_tw2 = nullptr;
   int* d_mod_lo = nullptr;
   int* d_mod_hi = nullptr;
+  void* d_mod_g = nullptr;  // fp16 [Ghi | Glo] operand of the tensor-core modulation spectrum
+  int mod_g_kp = 0;
   // grow-only workspace for the composite entry points
   void* ws = nullptr;
   size_t ws_bytes = 0;

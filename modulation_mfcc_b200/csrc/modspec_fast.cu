@@ -66,13 +66,16 @@ __global__ void __launch_bounds__(kModThreads)
     const float* src = mfcc + ((size_t)clip * n_coef + coef) * T + j * hop;
     float2 v[16];
     float sum = 0.0f;
+    // mean removal relative to a pivot (the window's first sample): next to a trajectory's offset (c0 sits
+    // near -500) the differences are small, so the fp32 sum keeps its digits
+    const float pivot = valid ? __ldg(src) : 0.0f;
 #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) {
       const int i0 = 2 * (tau + C::TPF * n2);
       float x0 = 0.0f, x1 = 0.0f;
       if (valid) {
-        if (i0 < win) x0 = __ldg(src + i0);
-        if (i0 + 1 < win) x1 = __ldg(src + i0 + 1);
+        if (i0 < win) x0 = __ldg(src + i0) - pivot;
+        if (i0 + 1 < win) x1 = __ldg(src + i0 + 1) - pivot;
       }
       v[n2] = make_float2(x0, x1);
       sum += x0 + x1;
@@ -266,11 +269,12 @@ __global__ void __launch_bounds__(kModThreads, 2)
       const int coef = valid[q] ? item[q] - w * n_coef : 0;
       const float* src = s_rows + coef * pitch + w * hop;
       float sum = 0.0f;
+      const float pivot = valid[q] ? src[0] : 0.0f;  // see modspec_fast_kernel
 #pragma unroll
       for (int n2 = 0; n2 < 16; ++n2) {
         const int i0 = 2 * (tau + C::TPF * n2);
-        const float x0 = (valid[q] && i0 < win) ? src[i0] : 0.0f;
-        const float x1 = (valid[q] && i0 + 1 < win) ? src[i0 + 1] : 0.0f;
+        const float x0 = (valid[q] && i0 < win) ? src[i0] - pivot : 0.0f;
+        const float x1 = (valid[q] && i0 + 1 < win) ? src[i0 + 1] - pivot : 0.0f;
         xs[q][2 * n2] = x0;
         xs[q][2 * n2 + 1] = x1;
         sum += x0 + x1;

@@ -413,6 +413,32 @@ def test_modspec_kernel_alone(cuda_device):
             assert np.allclose(band[i], rb, rtol=2e-6, atol=1e-6)
 
 
+def test_modspec_tensor_core_gemm(cuda_device):
+    """MMF_FLAG_TC_MODSPEC: windowing + DFT of 128 trajectory windows at a time as one tcgen05.mma kind::f16
+    GEMM (fp16 operand pairs, accumulators in tensor memory) -- same bounds as the FP32 kernel, against the
+    oracle on identical float32 input, including a trajectory with a large offset (c0 sits near -500),
+    chunked clips (hop 1), and shapes the GEMM path declines (they must fall through to the FP32 kernel)."""
+    torch = _torch()
+    rng = np.random.default_rng(12)
+    M = (rng.standard_normal((5, 13, 1001)).cumsum(axis=-1) * 0.5).astype(np.float32)
+    M[:, 0] -= 500.0
+    cfg = mm.plan.replace(_cfg("cfg1_16k")[0], flags=_lib.MMF_FLAG_TC_MODSPEC)
+    plan = mm.get_plan(cfg)
+    for (win_s, hop_s, fr) in [(1.0, 0.5, 100.0), (1.0, 0.01, 100.0), (0.77, 0.13, 100.0), (1.28, 0.5, 100.0),
+                               (2.0, 0.5, 200.0)]:
+        Lw, Hw, nfft, n_win = mm.modspec_sizes(1001, fr, win_s, hop_s)
+        bins = mm.band_bins(nfft, fr)
+        n0 = _lib.lib().mmf_launch_count(0)
+        mag, band = plan.modspec(torch.as_tensor(M).cuda(), Lw, Hw, nfft, bins)
+        assert _lib.lib().mmf_launch_count(0) - n0 == 1
+        mag, band = mag.cpu().numpy(), band.cpu().numpy()
+        for i in range(M.shape[0]):
+            rm, rb, _ = oracle.modulation_spectrum(M[i], fr, mod_win_s=win_s, mod_hop_s=hop_s)
+            assert mag[i].shape == rm.shape
+            assert np.max(np.abs(mag[i] - rm)) < ABS_TOL, (win_s, hop_s)
+            assert np.allclose(band[i], rb, rtol=2e-6, atol=1e-6), (win_s, hop_s)
+
+
 def test_get_velocity_and_filters(cuda_device):
     rng = np.random.default_rng(5)
     x = rng.standard_normal(777).cumsum()
