@@ -176,27 +176,35 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
     // ---- stage the trajectories this row block touches (coefficients c_lo .. c_hi), coalesced
     const int c_lo = r0 / wca, c_hi = min(r0 + kMtThreads - 1, n_items - 1) / wca;
     {
-      // eight independent loads per trajectory and thread in flight, two trajectories per step
+      // eight independent loads per trajectory and thread in flight, four trajectories per step (the loads
+      // of a step are all issued before its first store)
       const float* src0 = p.mfcc + ((size_t)clip * p.n_coef + c_lo) * p.T + w0 * p.hop;
       const int n_tr = c_hi - c_lo + 1;
-      for (int c = 0; c < n_tr; c += 2) {
-        const bool two = c + 1 < n_tr;
-        const float* ra = src0 + (size_t)c * p.T;
-        const float* rb = two ? ra + p.T : ra;
+      for (int c = 0; c < n_tr; c += 4) {
+        const float* r0 = src0 + (size_t)c * p.T;
+        const bool h1 = c + 1 < n_tr, h2 = c + 2 < n_tr, h3 = c + 3 < n_tr;
+        const float* r1 = h1 ? r0 + p.T : r0;
+        const float* r2 = h2 ? r0 + 2 * p.T : r0;
+        const float* r3 = h3 ? r0 + 3 * p.T : r0;
         for (int i0 = 0; i0 < span; i0 += 8 * kMtThreads) {
-          float a[8], b[8];
+          float a0[8], a1[8], a2[8], a3[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * kMtThreads + tid;
-            a[u] = i < span ? __ldg(ra + i) : 0.0f;
-            b[u] = (two && i < span) ? __ldg(rb + i) : 0.0f;
+            const bool in = i < span;
+            a0[u] = in ? __ldg(r0 + i) : 0.0f;
+            a1[u] = (in && h1) ? __ldg(r1 + i) : 0.0f;
+            a2[u] = (in && h2) ? __ldg(r2 + i) : 0.0f;
+            a3[u] = (in && h3) ? __ldg(r3 + i) : 0.0f;
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * kMtThreads + tid;
             if (i < span) {
-              s_buf[c * span + i] = a[u];
-              if (two) s_buf[(c + 1) * span + i] = b[u];
+              s_buf[c * span + i] = a0[u];
+              if (h1) s_buf[(c + 1) * span + i] = a1[u];
+              if (h2) s_buf[(c + 2) * span + i] = a2[u];
+              if (h3) s_buf[(c + 3) * span + i] = a3[u];
             }
           }
         }
