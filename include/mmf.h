@@ -66,8 +66,8 @@ typedef struct {
 #define MMF_FLAG_SEPARATE_MFCC 64 /* composite calls: clamp + DCT-II always as its own kernel */
 #define MMF_FLAG_TC_FFT 256       /* n_fft = 512: the transform as tcgen05.mma kind::f16 GEMMs (fp16 x3 operand split,
                                      accumulators in tensor memory); mmf_stft_power only so far */
-#define MMF_FLAG_TC_MODSPEC 512   /* modulation spectrum (win <= 128, nfft = 128) as a tcgen05.mma kind::f16 GEMM with TMEM
-                                     accumulators instead of the FP32 register FFT */
+#define MMF_FLAG_NO_TC_MODSPEC 512 /* modulation spectrum always with the FP32 register FFT (default for win <= 128,
+                                     nfft = 128: a tcgen05.mma kind::f16 GEMM with TMEM accumulators) */
 #define MMF_FLAG_FOLD_MFCC 128    /* composite calls: clamp + DCT-II inside the per-clip kernel even when delta is wanted
                                      (default: folded only when no delta output is requested; measured in DESIGN.md) */
 

@@ -55,7 +55,7 @@ MMF_FLAG_MMA_DCT = 32
 MMF_FLAG_SEPARATE_MFCC = 64
 MMF_FLAG_FOLD_MFCC = 128
 MMF_FLAG_TC_FFT = 256
-MMF_FLAG_TC_MODSPEC = 512
+MMF_FLAG_NO_TC_MODSPEC = 512
 
 
 class mmf_config(C.Structure):

@@ -134,7 +134,7 @@ static int ensure_mod_tables(mmf_plan* p, int win, int nfft, const int* lo, cons
       (e = upload(&p->d_mod_tw2, tw2)) != cudaSuccess || (e = upload(&p->d_mod_lo, vlo)) != cudaSuccess ||
       (e = upload(&p->d_mod_hi, vhi)) != cudaSuccess)
     return cuda_fail(e, "uploading modulation-spectrum tables");
-  if (modspec_tc_supported(win, nfft) && (p->cfg.flags & MMF_FLAG_TC_MODSPEC)) {
+  if (modspec_tc_supported(win, nfft) && !(p->cfg.flags & MMF_FLAG_NO_TC_MODSPEC)) {
     std::vector<uint16_t> g;
     uint16_t* d_g = nullptr;
     modspec_tc_table(win, nfft, g, &p->mod_g_kp);

@@ -413,16 +413,18 @@ def test_modspec_kernel_alone(cuda_device):
             assert np.allclose(band[i], rb, rtol=2e-6, atol=1e-6)
 
 
-def test_modspec_tensor_core_gemm(cuda_device):
-    """MMF_FLAG_TC_MODSPEC: windowing + DFT of 128 trajectory windows at a time as one tcgen05.mma kind::f16
-    GEMM (fp16 operand pairs, accumulators in tensor memory) -- same bounds as the FP32 kernel, against the
-    oracle on identical float32 input, including a trajectory with a large offset (c0 sits near -500),
-    chunked clips (hop 1), and shapes the GEMM path declines (they must fall through to the FP32 kernel)."""
+@pytest.mark.parametrize("flags", [0, _lib.MMF_FLAG_NO_TC_MODSPEC])
+def test_modspec_tensor_core_gemm(flags, cuda_device):
+    """Default for win <= 128, nfft = 128: windowing + DFT of 128 trajectory windows at a time as one
+    tcgen05.mma kind::f16 GEMM (fp16 operand pairs, accumulators in tensor memory); MMF_FLAG_NO_TC_MODSPEC
+    selects the FP32 register FFT.  Same bounds for both against the oracle on identical float32 input,
+    including a trajectory with a large offset (c0 sits near -500), chunked clips (hop 1), and shapes the
+    GEMM path declines (they fall through to the FP32 kernel)."""
     torch = _torch()
     rng = np.random.default_rng(12)
     M = (rng.standard_normal((5, 13, 1001)).cumsum(axis=-1) * 0.5).astype(np.float32)
     M[:, 0] -= 500.0
-    cfg = mm.plan.replace(_cfg("cfg1_16k")[0], flags=_lib.MMF_FLAG_TC_MODSPEC)
+    cfg = mm.plan.replace(_cfg("cfg1_16k")[0], flags=flags)
     plan = mm.get_plan(cfg)
     for (win_s, hop_s, fr) in [(1.0, 0.5, 100.0), (1.0, 0.01, 100.0), (0.77, 0.13, 100.0), (1.28, 0.5, 100.0),
                                (2.0, 0.5, 200.0)]:

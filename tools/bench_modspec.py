@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time the modulation-spectrum kernel alone on the bench shape (1024 clips x 13 x 1001, win 100, hop 50,
-nfft 128): FP32 register FFT (flags 0) vs tcgen05 GEMM (MMF_FLAG_TC_MODSPEC = 512).
+nfft 128): tcgen05 GEMM (flags 0, default) vs FP32 register FFT (MMF_FLAG_NO_TC_MODSPEC = 512).
 
     python tools/bench_modspec.py [--flags 0,512] [--iters 20]
 """
