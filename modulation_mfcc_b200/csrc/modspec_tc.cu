@@ -223,18 +223,20 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
       float v[KP];
       // mean removal relative to a pivot (the window's first sample): the differences are small next to a
       // trajectory's offset (c0 sits near -500), so the fp32 sum loses far less; four partial sums
-      const float pivot = valid ? x[0] : 0.0f;
+      // rows past the last item read row (c_lo, 0): finite data, results never stored.  win > 16 (KS - 1):
+      // only the last slab needs the k < win predicate
+      const float pivot = x[0];
       float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
-        v[k] = (valid && k < p.win) ? x[k] - pivot : 0.0f;
+        v[k] = (k < KP - 16 || k < p.win) ? x[k] - pivot : 0.0f;
         sum4[k & 3] += v[k];
       }
       const float mean = ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) * inv_win;
       float m = 0.0f;
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
-        v[k] = (k < p.win) ? v[k] - mean : 0.0f;
+        v[k] = (k < KP - 16 || k < p.win) ? v[k] - mean : 0.0f;
         m = fmaxf(m, fabsf(v[k]));
       }
       int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
@@ -317,7 +319,18 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     // ---- magnitudes out: rows are contiguous in memory wherever the coefficient does not change
-    if (p.mag != nullptr) {
+    if (p.mag != nullptr && wca == p.n_win) {
+      // the whole clip is one chunk: consecutive rows are consecutive output rows, the block is one flat
+      // stream of min(128, n_items - r0) * nb floats
+      float* dst = p.mag + (((size_t)clip * p.n_coef) * p.n_win + r0) * nb;
+      const int n_out = min(kMtThreads, n_items - r0) * nb;
+#pragma unroll 13
+      for (int e = tid; e < n_out; e += kMtThreads) {
+        float m;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(s_buf[e]));
+        dst[e] = m;
+      }
+    } else if (p.mag != nullptr) {
       // a warp writes its 32 rows one after the other, 65 consecutive floats per row; lane l holds row l's
       // destination and hands it round by shuffle (no dependent shared-memory load per row)
       const int lane = tid & 31;
