@@ -175,11 +175,33 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
   for (int r0 = 0; r0 < n_items; r0 += kMtThreads) {
     // ---- stage the trajectories this row block touches (coefficients c_lo .. c_hi), coalesced
     const int c_lo = r0 / wca, c_hi = min(r0 + kMtThreads - 1, n_items - 1) / wca;
-    {
+    // whole clip in one chunk and the touched trajectories fit with their own pitch T: one flat copy
+    const int n_tr = c_hi - c_lo + 1;
+    const bool flat_in = wca == p.n_win && (long)n_tr * p.T <= (long)kMtThreads * nb;
+    const int pitch = flat_in ? (int)p.T : span;
+    if (flat_in) {
+      const float* src0 = p.mfcc + ((size_t)clip * p.n_coef + c_lo) * p.T;
+      const int total = (n_tr - 1) * (int)p.T + span;
+      constexpr int kBatch = 33;  // 2 x 33 x 128 >= 128 * nb
+      for (int e0 = 0; e0 < total; e0 += kBatch * kMtThreads) {
+        float a[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          // clamped, not predicated: ptxas keeps a predicated load next to its store once it runs out of
+          // predicate registers, which serialises the latencies
+          const int e = min(e0 + u * kMtThreads + tid, total - 1);
+          a[u] = __ldg(src0 + e);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int e = e0 + u * kMtThreads + tid;
+          if (e < total) s_buf[e] = a[u];
+        }
+      }
+    } else {
       // eight independent loads per trajectory and thread in flight, four trajectories per step (the loads
       // of a step are all issued before its first store)
       const float* src0 = p.mfcc + ((size_t)clip * p.n_coef + c_lo) * p.T + w0 * p.hop;
-      const int n_tr = c_hi - c_lo + 1;
       for (int c = 0; c < n_tr; c += 4) {
         const float* r0 = src0 + (size_t)c * p.T;
         const bool h1 = c + 1 < n_tr, h2 = c + 2 < n_tr, h3 = c + 3 < n_tr;
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
     const int w = valid ? r - coef * wca : 0;
     float inv_s = 1.0f;
     {
-      const float* x = s_buf + (coef - c_lo) * span + w * p.hop;
+      const float* x = s_buf + (coef - c_lo) * pitch + w * p.hop;
       constexpr int KP = 16 * KS;
       float v[KP];
       // mean removal relative to a pivot (the window's first sample): the differences are small next to a
