@@ -68,6 +68,8 @@ typedef struct {
                                      accumulators in tensor memory); mmf_stft_power only so far */
 #define MMF_FLAG_NO_TC_MODSPEC 512 /* modulation spectrum always with the FP32 register FFT (default for win <= 128,
                                      nfft = 128: a tcgen05.mma kind::f16 GEMM with TMEM accumulators) */
+#define MMF_FLAG_TC_DCT 1024       /* clamp + DCT-II (+ delta) as a tcgen05.mma kind::f16 GEMM over 128-frame tiles
+                                     (n_mfcc <= 16, n_mels <= 96) instead of the FP32 FMA kernel; measured equal */
 #define MMF_FLAG_FOLD_MFCC 128    /* composite calls: clamp + DCT-II inside the per-clip kernel even when delta is wanted
                                      (default: folded only when no delta output is requested; measured in DESIGN.md) */
 

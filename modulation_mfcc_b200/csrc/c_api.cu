@@ -509,6 +509,16 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     return cuda_fail(e, "uploading plan constants");
   }
 
+  if ((cfg->flags & MMF_FLAG_TC_DCT) && !(cfg->flags & MMF_FLAG_MMA_DCT) && mfcc_tc_supported(cfg->n_mfcc, cfg->n_mels)) {
+    std::vector<uint16_t> tab;
+    uint16_t* d_t = nullptr;
+    mfcc_tc_table(dct.data(), cfg->n_mfcc, cfg->n_mels, tab, &p->dct_tc_kp);
+    if ((e = upload(&d_t, tab)) != cudaSuccess) {
+      mmf_plan_destroy(p);
+      return cuda_fail(e, "uploading the tensor-core DCT operand");
+    }
+    p->d_dct_tc = d_t;
+  }
   if ((cfg->flags & MMF_FLAG_TC_FFT) && tc_fft_supported(cfg->n_fft, cfg->hop_length, cfg->preemph)) {
     std::vector<uint16_t> btab;
     std::vector<float> twf;
@@ -540,6 +550,7 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaSetDevice(p->cfg.device);
   cudaDeviceSynchronize();
   cudaFree(p->d_window);
+  cudaFree(p->d_dct_tc);
   cudaFree(p->d_tc_btab);
   cudaFree(p->d_tc_tw);
   cudaFree(p->d_tw1);
@@ -720,6 +731,14 @@ int mmf_mfcc(mmf_plan* plan, float* logmel_dev, const int32_t* clipmax_dev, int6
     // Tensor-core DCT-II (mma.sync TF32 x3) on request only: measured 185 us against 95 us for the
     // FP32 kernel on the bench workload
     const bool mma = (plan->cfg.flags & MMF_FLAG_MMA_DCT) && mfcc_mma_supported(plan->cfg.n_mfcc, plan->cfg.n_mels);
+    if (!mma && plan->d_dct_tc != nullptr) {
+      // MMF_FLAG_TC_DCT: tcgen05 GEMM over 128-frame tiles (mfcc_tc.cu)
+      cudaError_t et = mfcc_tc_launch(plan->d_dct_tc, plan->dct_tc_kp, lm, clipmax_dev + c0, nc, T, plan->cfg.n_mels,
+                                      plan->cfg.n_mfcc, plan->cfg.top_db, mf, dl, clamp_in_place, plan->sm_count,
+                                      (cudaStream_t)stream);
+      if (et == cudaSuccess) continue;
+      if (et != cudaErrorNotSupported) return cuda_fail(et, "mfcc_tc_kernel launch");
+    }
     cudaError_t e = mma ? mfcc_mma_launch(plan->d_dct_bfrag, lm, clipmax_dev + c0, nc, T, plan->cfg.n_mels,
                                           plan->cfg.n_mfcc, plan->cfg.top_db, mf, dl, clamp_in_place, (cudaStream_t)stream)
                         : mfcc_launch(plan->d_dct, plan->nc_pad, lm, clipmax_dev + c0, nc, T, plan->cfg.n_mels,

@@ -79,6 +79,13 @@ cudaError_t tc_fft_power_launch(const float* pcm, long n_clips, long n_samples, 
                                 const float* window, const void* btab, const float2* tw, float* power, int sm_count,
                                 cudaStream_t st);
 
+// ---- clamp + DCT-II (+ delta) as a tcgen05 GEMM (mfcc_tc.cu)
+bool mfcc_tc_supported(int n_mfcc, int n_mels);
+void mfcc_tc_table(const float* dct, int n_mfcc, int n_mels, std::vector<uint16_t>& tab, int* kp_out);
+cudaError_t mfcc_tc_launch(const void* btab, int kp, float* logmel, const int* clipmax, long n_clips, long T, int n_mels,
+                           int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place, int sm_count,
+                           cudaStream_t st);
+
 // ---- modulation spectrum as a tcgen05 GEMM (modspec_tc.cu)
 bool modspec_tc_supported(int win, int nfft);
 void modspec_tc_table(int win, int nfft, std::vector<uint16_t>& g, int* kp_out);
@@ -218,6 +225,8 @@ struct mmf_plan {
   float4* d_dct_bfrag = nullptr;  // DCT B fragments of the tensor-core MFCC kernel
   int nc_pad = 0;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  void* d_dct_tc = nullptr;     // fp16 [Bhi ; Blo] operand of the tensor-core MFCC kernel
+  int dct_tc_kp = 0;
   void* d_tc_btab = nullptr;    // fp16 DFT operand tables of the tensor-core transform (MMF_FLAG_TC_FFT)
   float2* d_tc_tw = nullptr;
   // tables of the trajectory FFT, rebuilt when (win, nfft, bands) change

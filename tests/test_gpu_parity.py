@@ -123,6 +123,29 @@ def test_logmel_mfcc_delta(name, cuda_device):
         assert np.max(np.abs(dl[i] - np.gradient(M, axis=1))) < ABS_TOL, name
 
 
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_mfcc_fp32_and_tensor_core_kernels_agree(name, cuda_device):
+    """MMF_FLAG_TC_DCT (clamp + DCT-II as a tcgen05 GEMM with fp16 operand pairs; the FP32 FMA kernel for
+    shapes it declines) against the default FP32 FMA kernel and the oracle: MFCC, delta, clamped log-mel."""
+    cfg, secs = _cfg(name)
+    y = synth_batch(21, 3, int(cfg.sample_rate * secs) + 11, cfg.sample_rate)
+    out = []
+    for flags in (_lib.MMF_FLAG_TC_DCT, 0):
+        plan = mm.get_plan(mm.plan.replace(cfg, flags=flags))
+        lm, cmax = plan.logmel(y)
+        mf, dl = plan.mfcc(lm, cmax, delta=True, clamp_in_place=True)
+        mf2 = plan.mfcc(lm, cmax, delta=False, clamp_in_place=False)  # no halo, already clamped input
+        out.append((lm.cpu().numpy(), mf.cpu().numpy(), dl.cpu().numpy(), mf2.cpu().numpy()))
+    assert np.array_equal(out[0][0], out[1][0]), name  # the clamp itself is exact in both
+    assert np.max(np.abs(out[0][1] - out[1][1])) < 2e-4, name
+    assert np.max(np.abs(out[0][2] - out[1][2])) < 2e-4, name
+    assert np.max(np.abs(out[0][3] - out[0][1])) < 2e-4, name
+    for i in range(y.shape[0]):
+        M, inter, _ = _oracle_unclamped(y[i], cfg)
+        assert np.max(np.abs(out[0][1][i] - M)) < ABS_TOL, name
+        assert np.max(np.abs(out[0][2][i] - np.gradient(M, axis=1))) < ABS_TOL, name
+
+
 @pytest.mark.parametrize("name", ["cfg1_16k", "gui_default", "cfg3_44k", "n256"])
 def test_mfcc_tensor_core_variant(name, cuda_device):
     """MMF_FLAG_MMA_DCT: clamp + DCT-II (+ delta) through mma.sync TF32 x3 instead of FP32 FMAs."""
