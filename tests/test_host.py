@@ -36,6 +36,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.mmf_num_frames(100, 512, 50) == 3
 
 
+def test_flag_constants_match_header():
+    """Every MMF_FLAG_* of include/mmf.h has the same value in the ctypes binding, and all are distinct bits."""
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mmf.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (MMF_FLAG_\w+) (\d+)", hdr)}
+    assert len(flags) >= 11
+    for name, val in flags.items():
+        assert getattr(_lib, name) == val, name
+        assert val & (val - 1) == 0, name
+    assert len(set(flags.values())) == len(flags)
+
+
 def test_struct_layouts_match_header():
     lib = mm.lib()
     assert ctypes.sizeof(_lib.mmf_config) == lib.mmf_abi_sizeof(0)
