@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kDtThreads) mfcc_tc_kernel(const MfccTcArgs p)
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 32 * KP / 8; i += kDtThreads)
     reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(p.btab)[i];
-  constexpr int kCols = 128;  // D0 | D1 (32) + A hi (KP / 2 <= 32... up to 64) + A lo
+  constexpr int kCols = 128;  // D0 | D1 (32 columns) + A hi (KP / 2) + A lo (KP / 2), KP <= 96
   static_assert(32 + KP <= kCols, "TMEM budget");
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dt_smem_u32(&tmem_base)), "r"(kCols)
