@@ -161,9 +161,19 @@ __device__ __forceinline__ void warp_odd_ext_staged(double* buf, int T, int p, i
 template <typename TIn>
 __device__ __forceinline__ void warp_load_odd_ext(const TIn* __restrict__ x, int T, int p, double* buf, int S,
                                                   int lane) {
-  // interior: plain coalesced stream (unrolled so that several loads are in flight)
-#pragma unroll 8
-  for (int t = lane; t < T; t += 32) buf[p + t] = (double)x[t];
+  // interior: plain coalesced stream, eight loads in flight per lane.  The loads are unpredicated (index
+  // clamped to the row) -- with a predicated remainder loop ptxas put every load next to its store and the
+  // last 7 iterations of a 1001-sample row paid one memory latency each
+  for (int t0 = 0; t0 < T; t0 += 256) {
+    TIn a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = x[min(t0 + 32 * u + lane, T - 1)];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + 32 * u + lane;
+      if (t < T) buf[p + t] = (double)a[u];
+    }
+  }
   __syncwarp();
   warp_odd_ext_staged<TIn>(buf, T, p, S, lane);
 }
