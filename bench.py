@@ -380,7 +380,7 @@ def run_b200(args):
             "frames_per_clip": T,
             "l2": "inputs are 655 MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
             "collective": "one final all_gather_into_tensor of every step's totChange, inside the timed region" if world > 1 else "none",
-            "fp64_stages": "zero-phase Butterworth, derivative/norm and the trajectory FFT run in f64",
+            "fp64_stages": "zero-phase Butterworth and derivative/norm run in f64; the modulation spectrum is a tcgen05 GEMM (fp16 operand pairs, f32 accumulate)",
         },
         "clocks": clocks,
         "e2e": {
