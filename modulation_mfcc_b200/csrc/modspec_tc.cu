@@ -16,7 +16,7 @@
 // (A_hi against [Ghi_half ; Glo_half] -> D0 | D1) plus one N = 64 MMA (A_lo against Ghi_half -> D1).
 // A is written straight from registers into tensor memory (tcgen05.st, one TMEM lane per row), G is resident
 // in shared memory in the canonical K-major layout.  Descriptor formats and the split's
-// accuracy: tools/ubench/tcgen05_f16.cu, tools/ubench/tcgen05_tf32.cu (A from TMEM), tools/tf32_dft_study.py.
+// accuracy: tools/ubench/tcgen05_f16.cu, tools/ubench/tcgen05_tf32.cu (A from TMEM), tests/studies/tf32_dft_study.py.
 //
 // One CTA per (clip, chunk of windows) as in modspec_clip_kernel, rows in blocks of 128 ordered
 // (coefficient, window) so that consecutive rows are consecutive output rows; the per-row-block shared buffer

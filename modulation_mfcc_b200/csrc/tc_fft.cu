@@ -12,7 +12,7 @@
 //   D[:, 32:64] = hi . Rlo + lo . Rhi                            (second MMA, N = 32, accumulating)
 //   result      = (D[:, 0:32] + D[:, 32:64] / 2048) / s          -- 22-bit operands, fp32 accumulation
 //
-// tools/tf32_dft_study.py: mel-power error of this split 1.6e-6 (plain fp32 FFT: 1.6e-6); tools/ubench/
+// tests/studies/tf32_dft_study.py: mel-power error of this split 1.6e-6 (plain fp32 FFT: 1.6e-6); tools/ubench/
 // tcgen05_f16.cu: descriptors validated against the host, 48 + 47 cycles per K = 16 slab.
 //
 // Stage 1 A operand: K-major (thread (f, n1) owns a row and writes 16-byte chunks).  Stage 2 needs rows

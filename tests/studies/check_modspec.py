@@ -4,7 +4,7 @@ tcgen05 GEMM (flags 0, default) vs FP32 register FFT (MMF_FLAG_NO_TC_MODSPEC = 5
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

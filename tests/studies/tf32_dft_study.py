@@ -10,14 +10,14 @@ quantity the parity tests bound by 1e-4 (tests/test_gpu_parity.py LOGMEL_REL).  
 TF32 rate with the same 11-bit significand; its 5-bit exponent needs a power-of-two scale per frame and the
 low parts carried at 2^11 in their own accumulator ("fp16 x3").
 
-    python tools/tf32_dft_study.py            # CPU only, a few seconds
+    python tests/studies/tf32_dft_study.py            # CPU only, a few seconds
 """
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import mfcc_oracle as oracle  # noqa: E402  (host-side study, not a product path)
 from modulation_mfcc_b200.synth import synth_clip  # noqa: E402
 
@@ -152,9 +152,10 @@ def power_from_packed(Z):
     return X.real ** 2 + X.imag ** 2
 
 
-def main():
+def study(n_clips=4, seconds=2.0, verbose=True):
+    """-> {scheme: max relative error of the linear mel power}"""
     sr, n_fft, win, hop, n_mels = 16000, 512, 400, 160, 40
-    y = np.stack([synth_clip(s, sr * 2, sr) for s in range(4)])
+    y = np.stack([synth_clip(s, int(sr * seconds), sr) for s in range(n_clips)])
     w = oracle.padded_hann(win, n_fft).astype(np.float32)
     frames = []
     for clip in y:
@@ -166,13 +167,16 @@ def main():
     ref_pow = np.abs(np.fft.rfft(fr.astype(np.float64), axis=1)) ** 2
     ref_mel = ref_pow @ mel.T.astype(np.float64)
     z = (fr[:, 0::2] + 1j * fr[:, 1::2]).astype(np.complex64)
+    out = {}
 
     def report(name, powr):
         m = powr @ mel.T.astype(np.float64)
         rel = np.abs(m - ref_mel) / np.maximum(ref_mel, 1e-300)
         peak = ref_pow.max(axis=1, keepdims=True)
-        print(f"{name:>10}: mel power rel err max {rel.max():.2e}  p99.9 {np.quantile(rel, 0.999):.2e}  "
-              f"median {np.median(rel):.2e};  |P - ref| / frame peak max {np.max(np.abs(powr - ref_pow) / peak):.2e}")
+        out[name] = float(rel.max())
+        if verbose:
+            print(f"{name:>10}: mel power rel err max {rel.max():.2e}  p99.9 {np.quantile(rel, 0.999):.2e}  "
+                  f"median {np.median(rel):.2e};  |P - ref| / frame peak max {np.max(np.abs(powr - ref_pow) / peak):.2e}")
 
     import scipy.fft
 
@@ -180,6 +184,11 @@ def main():
     for scheme in PAIRS:
         report(scheme, power_from_packed(fft256_two_stage(z, scheme)))
     report("fp16 x3", power_from_packed(fft256_two_stage_f16(z)))
+    return out
+
+
+def main():
+    study()
 
 
 if __name__ == "__main__":

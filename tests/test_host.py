@@ -306,3 +306,19 @@ def test_emulated_sparse_mel_equals_dense(emu, cfg, bpw):
     emu.emu_mel(_p(P), 7, cfg.n_bins, seg_start.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(w2), cfg.n_mels, bpw, _p(out))
     ref = mel.astype(np.float64) @ P.astype(np.float64)
     assert np.max(np.abs(out - ref)) <= 2e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_operand_split_accuracy_study():
+    """Host emulation behind the tcgen05 kernels' operand format (tests/studies/tf32_dft_study.py): single TF32
+    operands miss the 1e-4 mel-power bound by far, the three-term TF32 split and the fp16 pair split (what
+    tc_fft.cu / modspec_tc.cu / mfcc_tc.cu use) sit at the fp32 FFT's own error."""
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "studies", "tf32_dft_study.py")
+    spec = importlib.util.spec_from_file_location("tf32_dft_study", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    err = mod.study(n_clips=1, seconds=0.5, verbose=False)
+    assert err["tf32 x1"] > 1e-4
+    assert err["tf32 x3"] < 1e-5 and err["fp16 x3"] < 1e-5
+    assert err["fp16 x3"] < 3 * err["fp32 FFT"]

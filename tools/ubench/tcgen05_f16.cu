@@ -1,5 +1,5 @@
 // Micro-benchmark + known-answer test: hand-written tcgen05.mma kind::f16 (fp16 operands, fp32
-// accumulate) on sm_100a -- the fp16 x3 alternative to the TF32 x3 split (tools/tf32_dft_study.py).
+// accumulate) on sm_100a -- the fp16 x3 alternative to the TF32 x3 split (tests/studies/tf32_dft_study.py).
 // Generated from tcgen05_tf32.cu's structure; same descriptors, 8 halves per 16-byte chunk, K = 16 per MMA.
 //
 //   D[128 x N] (TMEM, fp32) = A[128 x K] . B[N x K]^T,  A and B K-major in shared memory in the
