@@ -111,6 +111,11 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
     for f in ("script/mfcc.py", "script/calc.py"):
         assert "oracle" not in open(os.path.join(ROOT, f)).read()
+    # helper scripts under tools/ are not test infrastructure either (studies that need the oracle live in tests/studies)
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
 
 
 # ---------------------------------------------------------------------------
