@@ -20,6 +20,7 @@ from .plan import (  # noqa: F401
 from .api import (  # noqa: F401
     MODULATION_BANDS_HZ,
     FeatureExtractor,
+    ParameterError,
     applyFilter,
     band_bins,
     calculate_amplitude_envelope,

@@ -33,6 +33,21 @@ from .plan import MfccConfig, Plan, frame_sizes, get_plan, make_change_params
 MODULATION_BANDS_HZ = ((0.5, 2.0), (2.0, 4.0), (4.0, 8.0), (8.0, 16.0), (16.0, 32.0))
 
 
+class ParameterError(Exception):
+    """Stands in for ``librosa.util.exceptions.ParameterError`` (what ``librosa.feature.mfcc`` raises for
+    invalid audio at script/mfcc.py:387)."""
+
+
+def _require_float_audio(a):
+    """``librosa.util.valid_audio``: integer PCM is rejected, not silently rescaled.  (The corpus path for raw
+    16-bit samples is ``FeatureExtractor.host_call`` / ``mmf_features_host_pcm16``, which documents its 1/32768
+    scale.)"""
+    dt = getattr(a, "dtype", None)
+    is_float = dt is not None and (dt.is_floating_point if hasattr(dt, "is_floating_point") else np.issubdtype(dt, np.floating))
+    if not is_float:
+        raise ParameterError("Audio data must be floating-point")
+
+
 @lru_cache(maxsize=64)
 def _butter_sos_cached(order, wn, btype):
     return scipy.signal.butter(order, wn if not isinstance(wn, tuple) else list(wn), btype=btype, output="sos")
@@ -266,7 +281,7 @@ def applyFilter(x, sr, /, *, filt="iir", cutOff=[None], filtLen=6, filtType="low
 # ---------------------------------------------------------------------------
 
 
-def _read_audio(path: str, sr: float, device=None):
+def _read_audio(path: str, sr: float, device=None, *, to_host: bool = True):
     """Decode a WAV file to float32 in [-1, 1] shaped [channels, n] or [n] and bring
     it to ``sr`` (librosa.load(path, sr=sr, mono=False) at script/mfcc.py:373).
 
@@ -278,7 +293,12 @@ def _read_audio(path: str, sr: float, device=None):
     from scipy.io import wavfile
 
     torch = _torch()
-    file_sr, data = wavfile.read(path)
+    try:
+        file_sr, data = wavfile.read(path)
+    except ValueError as e:
+        # librosa.load goes through soundfile/audioread and also decodes FLAC, OGG, MP3 ...; here the
+        # container is parsed on the host and only RIFF/WAVE (PCM 8/16/32-bit, float32/64) is supported
+        raise ValueError(f"{path}: only RIFF/WAVE files can be decoded by the B200 loader ({e})") from None
     if data.ndim == 2:
         data = data.T
         if data.shape[0] == 1:
@@ -303,7 +323,7 @@ def _read_audio(path: str, sr: float, device=None):
             y = plan.resample_poly(y, fr.numerator, fr.denominator)
     except MmfError as e:
         _raise_from(e)
-    return np.ascontiguousarray(y.cpu().numpy())
+    return np.ascontiguousarray(y.cpu().numpy()) if to_host else y
 
 
 def load_channel(file_path: str, signal_sample_rate: float = 10_000, channel_nb: int = 0):
@@ -369,6 +389,9 @@ def get_MFCCS_change_batch(
     the result is returned as CUDA tensors).  Returns ``(totChange [B, T], T [T])``
     and, with ``return_features``, a dict with ``logmel``, ``mfcc``, ``delta``."""
     torch = _torch()
+    if not isinstance(audio, torch.Tensor):
+        audio = np.asarray(audio)
+    _require_float_audio(audio)
     plan = _change_setup(sigSr, tStep, winLen, n_mfcc, n_fft, minFreq, maxFreq, n_mels, preemph, device, flags)
     cutOffNorm = filtCutoff / ((1 / tStep) / 2)  # script/mfcc.py:398
     sos = _butter_sos(filtOrd, cutOffNorm, "low")  # script/mfcc.py:400
@@ -470,8 +493,9 @@ def get_MFCCS_change(
     Additive keywords (all default to the reference's behaviour): ``n_mels`` (the
     reference never passes it, so librosa's 128), ``preemph`` (0 = none),
     ``return_features``, ``device``.  Returns ``(totChange, T)`` as float64 arrays."""
-    if type(audioIn) == str:  # script/mfcc.py:372-373
-        myAudio = _read_audio(audioIn, sigSr)
+    from_file = type(audioIn) == str
+    if from_file:  # script/mfcc.py:372-373; the decoded, resampled audio stays on the device
+        myAudio = _read_audio(audioIn, sigSr, device, to_host=False)
     else:
         myAudio = audioIn
     if len(np.shape(myAudio)) > 1:  # script/mfcc.py:377-380
@@ -479,7 +503,7 @@ def get_MFCCS_change(
     else:
         y = myAudio
     out = get_MFCCS_change_batch(
-        np.asarray(y)[None, :],
+        y[None, :] if from_file else np.asarray(y)[None, :],
         sigSr,
         tStep=tStep,
         winLen=winLen,
@@ -501,12 +525,13 @@ def get_MFCCS_change(
         return_features=return_features,
         device=device,
     )
+    host = (lambda v: v.cpu().numpy()) if from_file else (lambda v: v)
     if return_features:
         tot, T, feats = out
-        feats = {k: (v[0] if v is not None else None) for k, v in feats.items()}
-        return (tot[0] if tot is not None else None), T, feats
+        feats = {k: (host(v[0]) if v is not None else None) for k, v in feats.items()}
+        return (host(tot[0]) if tot is not None else None), T, feats
     tot, T = out
-    return (tot[0] if tot is not None else None), T
+    return (host(tot[0]) if tot is not None else None), T
 
 
 # ---------------------------------------------------------------------------
@@ -515,16 +540,26 @@ def get_MFCCS_change(
 
 
 def get_velocity(x, sr, difference=1, method="gradient", width=3, accOrder=2, polyOrder=2, device=None):
-    """Drop-in for ``get_velocity`` (script/calc.py:593-650) for 1-D trajectories."""
+    """Drop-in for ``get_velocity`` (script/calc.py:593-650).
+
+    Like the reference, the derivative runs along axis 0 of ``x`` (``savgol_filter(axis=0)`` at calc.py:639,
+    ``FinDiff(0, ...)`` at :636); ``'gradient'`` on N-D input makes ``np.gradient`` return one array per axis,
+    which the reference then feeds back into ``np.gradient`` -- reproduced only for 1-D input, N-D raises."""
     if method not in ("finDiff", "sg", "gradient"):
         raise ValueError("Méthode inconnue. Utilisez 'gradient', 'sg' ou 'finDiff'.")
     torch = _torch()
-    xa = np.asarray(x) if not isinstance(x, torch.Tensor) else x
-    if xa.ndim != 1:
-        raise ValueError("get_velocity (B200): only 1-D trajectories are supported")
+    is_tensor = isinstance(x, torch.Tensor)
+    xa = x if is_tensor else np.asarray(x)
+    if xa.ndim == 0:
+        raise ValueError("get_velocity: x must have at least one dimension")
+    if xa.ndim > 1 and method == "gradient":
+        raise ValueError("get_velocity (B200): method='gradient' is supported for 1-D trajectories only")
     di = _device_index(device)
     plan = _any_plan(di)
     xd = _to_dev(xa, torch.float64, di)
+    nd = xd.dim()
+    if nd > 1:  # the kernels run along the last axis: bring axis 0 there
+        xd = xd.movedim(0, -1).contiguous()
     try:
         if method == "finDiff":
             coef, el, er = _findiff_stencil(int(difference), int(accOrder))
@@ -546,7 +581,9 @@ def get_velocity(x, sr, difference=1, method="gradient", width=3, accOrder=2, po
                 y = plan.stencil(y, *grad)
     except MmfError as e:
         _raise_from(e)
-    return y if isinstance(x, torch.Tensor) else y.cpu().numpy()
+    if nd > 1:
+        y = y.movedim(-1, 0).contiguous()
+    return y if is_tensor else y.cpu().numpy()
 
 
 # ---------------------------------------------------------------------------

@@ -66,6 +66,23 @@ static int ensure_ws(mmf_plan* p, size_t bytes) {
   return MMF_OK;
 }
 
+// The host-buffer entry points run on the plan's own streams: they get a workspace of their own so that
+// they never alias buffers of device-resident calls still in flight on the caller's stream.
+static int ensure_host_ws(mmf_plan* p, size_t bytes) {
+  if (bytes <= p->host_ws_bytes) return MMF_OK;
+  if (p->host_ws) {
+    MMF_CUDA(cudaStreamSynchronize(p->streams[0]));
+    MMF_CUDA(cudaStreamSynchronize(p->streams[1]));
+    MMF_CUDA(cudaFree(p->host_ws));
+    p->host_ws = nullptr;
+    p->host_ws_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&p->host_ws, bytes);
+  if (e != cudaSuccess) return fail(MMF_ERR_NOMEM, std::string("host-path workspace cudaMalloc: ") + cudaGetErrorString(e));
+  p->host_ws_bytes = bytes;
+  return MMF_OK;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // carve `bytes` out of a bump pointer
@@ -566,6 +583,7 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_dct);
   cudaFree(p->d_dct_bfrag);
   cudaFree(p->ws);
+  cudaFree(p->host_ws);
   cudaFree(p->d_mod_hann);
   cudaFree(p->d_mod_tw1);
   cudaFree(p->d_mod_tw2);
@@ -626,9 +644,11 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   a.mma_tile = p->d_mma_tile;
   a.mma_n_tiles = p->mma_n_tiles;
   a.mma_units = p->d_mma_units;
-  if (const char* e = std::getenv("MMF_DEBUG_SKIP")) a.debug_skip = std::atoi(e);
   a.early_tma = 1;
+#ifdef MMF_PROFILE  // profiling builds only: a stray environment variable must never change results
+  if (const char* e = std::getenv("MMF_DEBUG_SKIP")) a.debug_skip = std::atoi(e);
   if (const char* e = std::getenv("MMF_EARLY_TMA")) a.early_tma = std::atoi(e);
+#endif
   a.span_bufs = p->span_bufs;
   a.vec_ok = (c.hop_length % 2 == 0) ? 1 : 0;
   a.split_regs = (c.n_fft == 512 && !(c.flags & MMF_FLAG_SPLIT_SMEM)) ? 1 : 0;
@@ -683,8 +703,7 @@ static cudaError_t sosfiltfilt_any(const void* x, int x_is_f32, long rows, long 
   if (sos_par_fill(a, T, &par))
     return sosfiltfilt_par_launch(x, x_is_f32, rows, T, xs, group_rows, group_stride, par, y, ys, st);
   // long rows, few of them: the sequential kernel would walk every sample one by one
-  if (sos_long_supported(a, rows, T) && (size_t)rows * (size_t)(T + 2 * a.padlen) * 8 <= ((size_t)1 << 30) &&
-      !std::getenv("MMF_SOS_SEQUENTIAL"))
+  if (sos_long_supported(a, rows, T) && (size_t)rows * (size_t)(T + 2 * a.padlen) * 8 <= ((size_t)1 << 30))
     return sosfiltfilt_long_launch(x, x_is_f32, rows, T, xs, group_rows, group_stride, a, y, ys, st);
   return sosfiltfilt_launch_grouped(x, x_is_f32, rows, T, xs, group_rows, group_stride, a, y, ys, st);
 }
@@ -1044,14 +1063,20 @@ static int features_host_impl(mmf_plan* plan, const void* pcm_host_v, int pcm16,
   const size_t change_slot = change_ws_bytes(plan, chunk, T, true, !need_mfcc_dev, rows);
   const size_t raw_slot = pcm16 ? align_up((size_t)chunk * n_samples * 2, 256) : 0;  // int16 staging
   const size_t slot = pcm_slot + raw_slot + tot_slot + mfcc_slot + delta_slot + mag_slot + band_slot + change_slot;
-  int rc = ensure_ws(plan, (64 << 10) + 2 * slot);
+  int rc = ensure_host_ws(plan, (64 << 10) + 2 * slot);
   if (rc) return rc;
+  // the modulation tables are (re)built with a device-wide synchronisation: do it before any copy is queued
+  if (want_mod && n_win > 0 &&
+      (rc = ensure_mod_tables(plan, mod->win, mod->nfft, mod->band_lo, mod->band_hi, band_host ? mod->n_bands : 0)))
+    return rc;
+  // every exit below drains both streams: queued copies target caller-owned host buffers
+  auto body = [&]() -> int {
   int64_t done = 0;
   for (int i = 0; done < n_clips; ++i, done += chunk) {
     const int s = i & 1;
     const int64_t nc = std::min<int64_t>(chunk, n_clips - done);
     cudaStream_t st = plan->streams[s];
-    unsigned char* cur = (unsigned char*)plan->ws + (64 << 10) + (size_t)s * slot;
+    unsigned char* cur = (unsigned char*)plan->host_ws + (64 << 10) + (size_t)s * slot;
     float* d_pcm = (float*)cur;
     cur += pcm_slot;
     int16_t* d_raw = pcm16 ? (int16_t*)cur : nullptr;
@@ -1108,8 +1133,14 @@ static int features_host_impl(mmf_plan* plan, const void* pcm_host_v, int pcm16,
       MMF_CUDA(cudaMemcpyAsync(band_host + (size_t)done * n_win * mod->n_bands, d_band,
                                (size_t)nc * n_win * mod->n_bands * 4, cudaMemcpyDeviceToHost, st));
   }
-  MMF_CUDA(cudaStreamSynchronize(plan->streams[0]));
-  MMF_CUDA(cudaStreamSynchronize(plan->streams[1]));
+  return MMF_OK;
+  };
+  rc = body();
+  const cudaError_t e0 = cudaStreamSynchronize(plan->streams[0]);
+  const cudaError_t e1 = cudaStreamSynchronize(plan->streams[1]);
+  if (rc) return rc;
+  if (e0 != cudaSuccess) return cuda_fail(e0, "host path, stream 0");
+  if (e1 != cudaSuccess) return cuda_fail(e1, "host path, stream 1");
   return MMF_OK;
 }
 

@@ -242,6 +242,8 @@ struct mmf_plan {
   // grow-only workspace for the composite entry points
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  void* host_ws = nullptr;  // workspace of the host-buffer entry points (they run on `streams`)
+  size_t host_ws_bytes = 0;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaStream_t streams[2] = {nullptr, nullptr};

@@ -9,6 +9,7 @@ memory and streams only; all arithmetic happens in ``libmmf_b200.so``).
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
 from dataclasses import dataclass, replace
 
 import numpy as np
@@ -589,47 +590,58 @@ class Plan:
         return out
 
     def mfcc_change_host(self, pcm_host: np.ndarray, prm: mmf_change_params, *, want_mfcc: bool = False):
-        """Host buffers in and out through the single C-ABI call (H2D/D2H inside)."""
+        """Host buffers in and out through the single C-ABI call (H2D/D2H inside).
+
+        float32 samples go through ``mmf_mfcc_change_host``; int16 samples (raw WAV PCM) through
+        ``mmf_features_host_pcm16``, which scales them by 1/32768 on the device."""
         pcm_host = np.asarray(pcm_host)
-        pcm16 = pcm_host.dtype == np.int16  # raw WAV samples: scaled by 1/32768 on the device
+        pcm16 = pcm_host.dtype == np.int16
         if not pcm16 and pcm_host.dtype != np.float32:
             pcm_host = pcm_host.astype(np.float32)
         if pcm_host.ndim == 1:
             pcm_host = pcm_host[None, :]
         isz = pcm_host.dtype.itemsize
-        if pcm_host.strides[1] != isz:
+        if pcm_host.strides[1] != isz or pcm_host.strides[0] % isz:
             pcm_host = np.ascontiguousarray(pcm_host)
         B, N = pcm_host.shape
         T = self.num_frames(N)
         tot = np.empty((B, T), np.float64)
         mf = np.empty((B, self.cfg.n_mfcc, T), np.float32) if want_mfcc else None
-        check(
-            _lib.lib().mmf_mfcc_change_host(
-                self._h,
-                pcm_host.ctypes.data,
-                B,
-                N,
-                pcm_host.strides[0] // 4 if B > 1 else N,
-                C.byref(prm),
-                tot.ctypes.data,
-                mf.ctypes.data if want_mfcc else None,
+        stride = pcm_host.strides[0] // isz if B > 1 else N
+        if pcm16:
+            check(
+                _lib.lib().mmf_features_host_pcm16(
+                    self._h, pcm_host.ctypes.data, B, N, stride, C.byref(prm), None, tot.ctypes.data,
+                    mf.ctypes.data if want_mfcc else None, None, None, None,
+                )
             )
-        )
+        else:
+            check(
+                _lib.lib().mmf_mfcc_change_host(
+                    self._h, pcm_host.ctypes.data, B, N, stride, C.byref(prm), tot.ctypes.data,
+                    mf.ctypes.data if want_mfcc else None,
+                )
+            )
         return (tot, mf) if want_mfcc else tot
 
 
-_PLANS: dict[MfccConfig, Plan] = {}
+_PLANS: "OrderedDict[MfccConfig, Plan]" = OrderedDict()
+_MAX_PLANS = 16
 
 
 def get_plan(cfg: MfccConfig) -> Plan:
-    """Keyed cache of plans (window, mel bank, DCT, twiddles stay on the device)."""
+    """Keyed least-recently-used cache of plans (window, mel bank, DCT, twiddles stay on the device).
+
+    An evicted plan is only dropped from the cache: objects that still hold it (a ``FeatureExtractor``, a
+    caller's local) keep a live handle, and ``Plan.__del__`` frees the device memory with the last reference."""
     p = _PLANS.get(cfg)
     if p is None:
-        if len(_PLANS) >= 16:
-            _, old = _PLANS.popitem()
-            old.close()
+        while len(_PLANS) >= _MAX_PLANS:
+            _PLANS.popitem(last=False)
         p = Plan(cfg)
         _PLANS[cfg] = p
+    else:
+        _PLANS.move_to_end(cfg)
     return p
 
 

@@ -327,3 +327,38 @@ def test_operand_split_accuracy_study():
     assert err["tf32 x1"] > 1e-4
     assert err["tf32 x3"] < 1e-5 and err["fp16 x3"] < 1e-5
     assert err["fp16 x3"] < 3 * err["fp32 FFT"]
+
+
+def test_plan_cache_is_lru_and_never_closes_live_plans(monkeypatch):
+    """the plan cache must evict the least recently used entry and must not close() a plan
+    that another object may still hold (device memory goes with the last reference)."""
+    from modulation_mfcc_b200 import plan as plan_mod
+
+    closed = []
+
+    class FakePlan:
+        def __init__(self, cfg):
+            self.cfg = cfg
+
+        def close(self):
+            closed.append(self.cfg)
+
+    monkeypatch.setattr(plan_mod, "Plan", FakePlan)
+    monkeypatch.setattr(plan_mod, "_PLANS", type(plan_mod._PLANS)())
+    cfgs = [mm.MfccConfig(8000.0 + i) for i in range(plan_mod._MAX_PLANS + 3)]
+    first = plan_mod.get_plan(cfgs[0])
+    for c in cfgs[1 : plan_mod._MAX_PLANS]:
+        plan_mod.get_plan(c)
+    assert plan_mod.get_plan(cfgs[0]) is first  # refreshes cfgs[0]
+    for c in cfgs[plan_mod._MAX_PLANS :]:
+        plan_mod.get_plan(c)
+    assert len(plan_mod._PLANS) == plan_mod._MAX_PLANS
+    assert cfgs[0] in plan_mod._PLANS  # most recently used survived
+    assert cfgs[1] not in plan_mod._PLANS and cfgs[2] not in plan_mod._PLANS and cfgs[3] not in plan_mod._PLANS
+    assert closed == []  # evicted plans are dropped, not closed
+
+
+def test_integer_audio_is_rejected_before_any_gpu_work():
+    """librosa.util.valid_audio semantics under script/mfcc.py:387."""
+    with pytest.raises(mm.ParameterError, match="floating-point"):
+        mm.get_MFCCS_change(np.zeros(4000, np.int16), 10000, outFiltCutOff=[12])
