@@ -70,6 +70,8 @@ typedef struct {
                                      nfft = 128: a tcgen05.mma kind::f16 GEMM with TMEM accumulators) */
 #define MMF_FLAG_TC_DCT 1024       /* clamp + DCT-II (+ delta) as a tcgen05.mma kind::f16 GEMM over 128-frame tiles
                                      (n_mfcc <= 16, n_mels <= 96) instead of the FP32 FMA kernel; measured equal */
+#define MMF_FLAG_MEL_WALK 2048     /* mel projection with the per-bin sparse walk on the [bin][frame] power tile instead of
+                                      the grouped walk (four bins per step, packed FFMA2) on the bin-pair tile */
 #define MMF_FLAG_FOLD_MFCC 128    /* composite calls: clamp + DCT-II inside the per-clip kernel even when delta is wanted
                                      (default: folded only when no delta output is requested; measured in DESIGN.md) */
 

@@ -57,6 +57,7 @@ MMF_FLAG_FOLD_MFCC = 128
 MMF_FLAG_TC_FFT = 256
 MMF_FLAG_NO_TC_MODSPEC = 512
 MMF_FLAG_TC_DCT = 1024
+MMF_FLAG_MEL_WALK = 2048
 
 
 class mmf_config(C.Structure):

@@ -290,6 +290,12 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     return fail(MMF_ERR_UNSUPPORTED, "mel filterbank is not a two-slope (triangular) bank");
   }
   host_dct(cfg->n_mfcc, cfg->n_mels, dct);
+  // grouped mel walk on the bin-pair power tile: the default; MMF_FLAG_MEL_WALK / MMF_FLAG_MMA_MEL select
+  // the [bin][frame] tile with the sparse walk / the mma.sync projection
+  MelGroups mg;
+  host_mel_groups(sp, p->F, cfg->n_mels, mg);
+  p->mel_groups = (cfg->flags & (MMF_FLAG_MEL_WALK | MMF_FLAG_MMA_MEL)) ? 0 : 1;
+  p->mg_n = mg.n_groups;
 
   // ---- tensor-core mel tables.  An n-tile is a run of up to 8 consecutive bands (the N of
   // mma.m16n8k8); it is cut short when its bands span more than kTileBlocks k-tiles of 8 bins, so
@@ -342,6 +348,9 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   // (<= 113 KB each: 227 KB per SM, 1 KB reserved per CTA); one CTA per SM as the last resort.
   const int fpw = p->geo.tpf < 32 ? 32 / p->geo.tpf : 1;  // frames per warp in the FFT phase
   auto pitch_for = [&](int tf) {
+    // bin-pair layout: 8-byte words per bin-pair row; = 2 (mod 16) keeps the 32-bit stores of the two
+    // thread groups of a warp on disjoint banks (stft_core.cuh: TilePairs)
+    if (p->mel_groups) return std::max(tf, 2) + 2;
     if (p->packed) {
       // two-frame path: 64-bit stores of (frame, frame+1) pairs by consecutive bins:
       // pitch == 2 (mod 4) keeps them 8-byte aligned and conflict-free per half-warp
@@ -368,7 +377,8 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     const int span = (tf - 1) * cfg->hop_length + cfg->n_fft + p->lead + 3;
     const int alloc = (span + 255) / 256 * 256;
     return stft_smem_bytes(cfg->n_fft, alloc, span_bufs, pitch_for(tf), pt_bufs, p->packed,
-                           stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, mel_mma, p->mma_n_pairs, NT), threads);
+                           stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, mel_mma, p->mma_n_pairs, NT, p->mel_groups, p->mg_n),
+                           threads, p->mel_groups);
   };
   auto fpi_for = [&](int threads) { return (threads / p->geo.tpf) * (p->packed ? 2 : 1); };
   // widest tile (then most double buffering) that fits `budget` with CTAs of `threads`
@@ -442,7 +452,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   p->ctas_per_sm = g.ctas;
   p->ppitch = pitch_for(tf);
   p->smem = g.smem;
-  p->mel_tab_bytes = stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, p->mel_mma, p->mma_n_pairs, NT);
+  p->mel_tab_bytes = stft_mel_table_bytes(cfg->n_fft, cfg->n_mels, p->mel_mma, p->mma_n_pairs, NT, p->mel_groups, p->mg_n);
   p->mma_n_tiles = NT;
 
   // ---- tensor-core mel work list: unit = (n-tile, 16-frame m-tile), cost = blocks of the n-tile;
@@ -477,7 +487,9 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   {
     const int workers = std::min(256, (p->threads / 32) * (32 / tf));
     const int cbin = 7, cband = 48;  // measured: 7 instructions per bin, 29 per segment + 19 per band
-    auto group_cost = [&](int a, int b) {  // bands [a, b): segments a..b
+    const int cgroup = 14, cseg = 41;  // grouped walk (SASS count): per 4-bin weight group, per segment
+    auto group_cost = [&](int a, int b) -> long {  // bands [a, b): segments a..b
+      if (p->mel_groups) return (long)cgroup * (mg.segtab[2 * (b + 1) + 1] - mg.segtab[2 * a + 1]) + (long)cseg * (b - a + 1);
       return cbin * (sp.seg_start[b + 1] - sp.seg_start[a]) + cband * (b - a);
     };
     auto fill = [&](long bound, std::vector<int>* out) {
@@ -514,6 +526,20 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   std::vector<float4> dct_bfrag;
   mfcc_mma_bfrag(dct.data(), cfg->n_mfcc, cfg->n_mels, dct_bfrag);
   cudaError_t e;
+  {
+    std::vector<int2> segtab(cfg->n_mels + 2);
+    for (int j = 0; j < cfg->n_mels + 2; ++j) segtab[j] = make_int2(mg.segtab[2 * j], mg.segtab[2 * j + 1]);
+    std::vector<float4> w4((size_t)2 * mg.n_groups);
+    for (size_t i = 0; i < w4.size(); ++i) w4[i] = make_float4(mg.w[4 * i], mg.w[4 * i + 1], mg.w[4 * i + 2], mg.w[4 * i + 3]);
+    std::vector<int2> segstep(cfg->n_mels + 3);
+    for (int j = 0; j < cfg->n_mels + 3; ++j)  // step in 8-byte tile words: two bin-pair rows per group
+      segstep[j] = make_int2(mg.segstep[2 * j], mg.segstep[2 * j + 1] * 2 * p->ppitch);
+    if ((e = upload(&p->d_mg_seg, segtab)) != cudaSuccess || (e = upload(&p->d_mg_w, w4)) != cudaSuccess ||
+        (e = upload(&p->d_mg_step, segstep)) != cudaSuccess) {
+      mmf_plan_destroy(p);
+      return cuda_fail(e, "uploading the grouped mel tables");
+    }
+  }
   if ((e = upload(&p->d_dct_bfrag, dct_bfrag)) != cudaSuccess || (e = upload(&p->d_window, window)) != cudaSuccess || (e = upload(&p->d_tw1, tw1)) != cudaSuccess ||
       (e = upload(&p->d_tw2, tw2)) != cudaSuccess || (e = upload(&p->d_seg, sp.seg_start)) != cudaSuccess ||
       (e = upload(&p->d_band_split, band_split)) != cudaSuccess ||
@@ -580,6 +606,9 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_mma_tile);
   cudaFree(p->d_mma_units);
   cudaFree(p->d_w2);
+  cudaFree(p->d_mg_seg);
+  cudaFree(p->d_mg_step);
+  cudaFree(p->d_mg_w);
   cudaFree(p->d_dct);
   cudaFree(p->d_dct_bfrag);
   cudaFree(p->ws);
@@ -661,6 +690,11 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   a.seg_start = p->d_seg;
   a.band_split = p->d_band_split;
   a.w2 = p->d_w2;
+  a.mel_groups = p->mel_groups;
+  a.mg_n = p->mg_n;
+  a.mg_seg = p->d_mg_seg;
+  a.mg_step = p->d_mg_step;
+  a.mg_w = p->d_mg_w;
   a.logmel = logmel;
   a.clipmax = clipmax;
   a.power = power;

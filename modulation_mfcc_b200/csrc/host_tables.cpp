@@ -102,6 +102,40 @@ bool host_mel_sparse(const std::vector<float>& mel, const std::vector<double>& m
   return true;
 }
 
+// Grouped form of the sparse bank for the packed mel walk (stft_core.cuh: mel_groups): segment j is
+// covered by groups of four consecutive bins aligned to multiples of four; the falling / rising weights of a
+// group's bins are stored densely, zero outside the segment.
+void host_mel_groups(const MelSparse& sp, int F, int n_mels, MelGroups& out) {
+  out.segtab.assign((size_t)2 * (n_mels + 2), 0);
+  out.segstep.assign((size_t)2 * (n_mels + 3), 0);
+  out.w.clear();
+  int widx = 0;
+  int pos = 0;  // group the walk stands on after the previous segment
+  for (int j = 0; j <= n_mels + 1; ++j) {
+    const int a = sp.seg_start[j];
+    const int b = j <= n_mels ? sp.seg_start[j + 1] : a;
+    const int g0 = a / 4, g1 = b > a ? (b + 3) / 4 : g0;
+    out.segtab[2 * j] = g0;
+    out.segtab[2 * j + 1] = widx;
+    out.segstep[2 * j] = g1 - g0;               // groups of segment j
+    out.segstep[2 * j + 1] = j ? g0 - pos : 0;  // groups to step before it (-1 or 0)
+    pos = g1;
+    for (int g = g0; g < g1; ++g) {
+      float dn[4], up[4];
+      for (int i = 0; i < 4; ++i) {
+        const int k = 4 * g + i;
+        const bool in = k >= a && k < b && k < F;
+        dn[i] = in ? sp.w2[2 * k] : 0.0f;
+        up[i] = in ? sp.w2[2 * k + 1] : 0.0f;
+      }
+      out.w.insert(out.w.end(), dn, dn + 4);
+      out.w.insert(out.w.end(), up, up + 4);
+      ++widx;
+    }
+  }
+  out.n_groups = widx;
+}
+
 void host_dct(int n_mfcc, int n_mels, std::vector<float>& d) {
   d.resize((size_t)n_mfcc * n_mels);
   for (int k = 0; k < n_mfcc; ++k)

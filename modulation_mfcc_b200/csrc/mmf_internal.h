@@ -55,6 +55,11 @@ struct StftArgs {
   const int* seg_start;  // [n_mels + 2]
   const int* band_split; // [257] first band of each mel worker (balanced band groups), padded with n_mels
   const float2* w2;      // [F] (falling, rising) mel weights per bin
+  int mel_groups;        // grouped mel walk on the bin-pair tile layout (default) instead of the sparse walk
+  int mg_n;              // weight groups of the grouped walk
+  const int2* mg_seg;    // [n_mels + 2] (first 4-bin group, first weight group) per segment
+  const int2* mg_step;   // [n_mels + 3] (weight groups, tile-pointer step in 8-byte words before the segment)
+  const float4* mg_w;    // [2 * mg_n] falling / rising weights of each group
   float* logmel;         // [n_clips, n_mels, T] or null
   int* clipmax;          // [n_clips] float keys or null
   float* power;          // [n_clips, F, T] or null
@@ -66,9 +71,10 @@ struct StftGeometry {
 
 bool stft_packed_supported(int n_fft);
 int stft_geometry(int n_fft, int packed, int threads, StftGeometry* g);
-size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int n_tiles);
+size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int n_tiles, int mel_groups = 0,
+                            int mg_n = 0);
 size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed,
-                       size_t mel_tab_bytes, int threads);
+                       size_t mel_tab_bytes, int threads, int mel_groups = 0);
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
                             cudaStream_t st);
 
@@ -176,6 +182,13 @@ void host_mel_dense(double sr, int n_fft, int n_mels, double fmin, double fmax, 
                     std::vector<double>& mel_f);
 bool host_mel_sparse(const std::vector<float>& mel, const std::vector<double>& mel_f, double sr, int n_fft, int n_mels,
                      MelSparse& out);
+struct MelGroups {
+  std::vector<int> segtab;  // (first 4-bin group, first weight group) per segment, n_mels + 2 entries
+  std::vector<int> segstep; // (groups of the segment, groups to step back before it) per segment, n_mels + 3 entries
+  std::vector<float> w;     // 8 floats per weight group: 4 falling, 4 rising
+  int n_groups = 0;
+};
+void host_mel_groups(const MelSparse& sp, int F, int n_mels, MelGroups& out);
 void host_dct(int n_mfcc, int n_mels, std::vector<float>& d);
 void host_twiddles(int n_fft, const StftGeometry& g, std::vector<float2>& tw1, std::vector<float2>& tw2);
 int host_sos_zi(const double* sos, int n_sections, double* zi, int* padlen);
@@ -221,6 +234,10 @@ struct mmf_plan {
   int mma_n_pairs = 0;
   size_t mel_tab_bytes = 0;
   float2* d_w2 = nullptr;
+  int mel_groups = 0, mg_n = 0;  // grouped mel walk (bin-pair power tile)
+  int2* d_mg_seg = nullptr;
+  int2* d_mg_step = nullptr;
+  float4* d_mg_w = nullptr;
   float* d_dct = nullptr;  // [n_mels][nc_pad]
   float4* d_dct_bfrag = nullptr;  // DCT B fragments of the tensor-core MFCC kernel
   int nc_pad = 0;

@@ -37,6 +37,7 @@ namespace {
 
 constexpr int kMtThreads = 128;
 constexpr int kMtKMax = 128;  // win <= 128
+constexpr long kMtSmemLimit = 110 * 1024;  // dynamic shared memory per CTA (two CTAs per SM)
 
 __device__ __forceinline__ uint32_t mt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -447,7 +448,10 @@ cudaError_t modspec_tc_launch(const float* mfcc, long n_clips, int n_coef, long 
   auto fits = [&](long w) {
     const long span = (w - 1) * hop + win;
     const long n_tr = std::min<long>(n_coef, (kMtThreads - 1) / w + 2);
-    return n_tr * span <= (long)kMtThreads * nb && w * n_coef * std::max(n_bands, 1) * 4 <= 24 * 1024;
+    // dynamic shared memory of a CTA: operand table + staging buffer + row pointers + band table, within the
+    // 110 KB the kernel opts into (two CTAs per SM) less its static variables
+    const long fixed = 2L * nfft * kp * 2 + (long)kMtThreads * nb * 4 + (long)kMtThreads * (long)sizeof(float*);
+    return n_tr * span <= (long)kMtThreads * nb && fixed + w * n_coef * std::max(n_bands, 1) * 4 <= kMtSmemLimit - 512;
   };
   while (wc > 1 && !fits(wc)) wc = (wc + 1) / 2;
   if (!fits(wc)) return cudaSuccess;
@@ -476,7 +480,7 @@ cudaError_t modspec_tc_launch(const float* mfcc, long n_clips, int n_coef, long 
 #define MMF_MT_CASE(KS)                                                            \
   case KS: {                                                                       \
     auto kfn = modspec_tc_kernel<128, KS>;                                         \
-    MMF_SMEM_ONCE(kfn, 110 * 1024);                                                \
+    MMF_SMEM_ONCE(kfn, kMtSmemLimit);                                              \
     kfn<<<(unsigned)std::min<long>(a.n_work, 2L * sm_count), kMtThreads, smem, st>>>(a); \
     break;                                                                         \
   }

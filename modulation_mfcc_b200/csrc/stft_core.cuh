@@ -289,24 +289,58 @@ MMF_HD V split_pair(V a, V b, float2 c32r, typename CxTraits<V>::Tw wtau) {
 MMF_HD void ptile_store(float* ptile, int idx, float p) { ptile[idx] = p; }
 MMF_HD void ptile_store(float* ptile, int idx, pk p) { *reinterpret_cast<pk*>(ptile + idx) = p; }
 
+// ---- power-tile layouts (where the split step puts |X[k]|^2 of frame t)
+// TileRows: [k][t], `pitch` floats per bin row -- read by the sparse mel walk (one frame per lane, one
+// 32-bit load per bin) and by the mma.sync mel.
+struct TileRows {
+  float* base;
+  int pitch;
+  MMF_HD void put(int k, int t, float p) const { base[k * pitch + t] = p; }
+  MMF_HD void put(int k, int t, pk p) const { *reinterpret_cast<pk*>(base + k * pitch + t) = p; }  // frames t, t+1
+  MMF_HD float get(int k, int t) const { return base[k * pitch + t]; }
+};
+// TilePairs: [k / 2][column][k & 1] -- bins 2q and 2q+1 of ONE frame share an 8-byte word, so the mel
+// phase reads two bins per 64-bit load and feeds them to one packed FFMA2 against two weights.  `pitch` =
+// 8-byte words per bin-pair row.  Two-frame thread groups hold frames t (even) and t+1: they go to columns
+// t/2 and t/2 + half (half = frames per tile / 2), which keeps the 32-bit stores of the two thread groups of
+// a warp on disjoint banks when pitch = 2 (mod 16).
+struct TilePairs {
+  float* base;
+  int pitch;
+  int half;
+  MMF_HD int col(int t, bool two_frames) const { return two_frames ? (t >> 1) + (t & 1) * half : t; }
+  MMF_HD void put(int k, int t, float p) const { base[(((k >> 1) * pitch + t) << 1) + (k & 1)] = p; }
+  MMF_HD void put(int k, int t, pk p) const {
+    float* q = base + ((((k >> 1) * pitch) + (t >> 1)) << 1) + (k & 1);
+    q[0] = plo(p);
+    q[2 * half] = phi(p);
+  }
+  MMF_HD float get(int k, int t, bool two_frames) const { return base[(((k >> 1) * pitch + col(t, two_frames)) << 1) + (k & 1)]; }
+};
+
 // ---- split step from gathered pairs (any NFFT).
 // Thread tau handles k = tau + TPF*r, r = 0..7 (covers [0, M/2)); tau == 0 also k = M/2.
-// Power lands in ptile[k*ppitch + t].
-template <int NFFT, typename V>
-MMF_HD void ph_split_pairs(const V (&a)[9], const V (&b)[8], float* ptile, int ppitch, int t, int tau,
-                           typename CxTraits<V>::Tw wtau) {
+// Power of bin k goes to st.put(k, t, power).
+template <int NFFT, typename V, typename Tile>
+MMF_HD void ph_split_pairs_to(const V (&a)[9], const V (&b)[8], const Tile& st, int t, int tau,
+                              typename CxTraits<V>::Tw wtau) {
   using C = FftCfg<NFFT>;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int k = tau + C::TPF * r;
     const V p = split_pair(a[r], b[r], w32(r), wtau);
-    ptile_store(ptile, k * ppitch + t, p.x);
-    ptile_store(ptile, (C::M - k) * ppitch + t, p.y);
+    st.put(k, t, p.x);
+    st.put(C::M - k, t, p.y);
   }
   if (tau == 0) {
     const V p = split_pair(a[8], a[8], w32(8), wtau);
-    ptile_store(ptile, (C::M / 2) * ppitch + t, p.x);
+    st.put(C::M / 2, t, p.x);
   }
+}
+template <int NFFT, typename V>
+MMF_HD void ph_split_pairs(const V (&a)[9], const V (&b)[8], float* ptile, int ppitch, int t, int tau,
+                           typename CxTraits<V>::Tw wtau) {
+  ph_split_pairs_to<NFFT>(a, b, TileRows{ptile, ppitch}, t, tau, wtau);
 }
 
 // one-frame convenience used by the host emulator and the trajectory-FFT kernel
@@ -342,21 +376,26 @@ MMF_HD void ph_split_smem_cb(const float2* xb, int tau, float2 wtau, Emit emit) 
 // s = tau holds Z[16*j2 + s] in v[j2].  bpart[r] must hold Z[M - (16*r + s)]:
 // on the device it is v[15 - r] of lane (16 - s) & 15 (one shuffle per float);
 // for s == 0 it is the thread's own v[(16 - r) & 15].
-template <typename V>
-MMF_HD void ph_split_regs512(const V (&v)[16], const V (&bpart)[8], float* ptile, int ppitch, int t, int s,
-                             typename CxTraits<V>::Tw wtau) {
+template <typename V, typename Tile>
+MMF_HD void ph_split_regs512_to(const V (&v)[16], const V (&bpart)[8], const Tile& st, int t, int s,
+                                typename CxTraits<V>::Tw wtau) {
   constexpr int M = 256;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int k = 16 * r + s;
     const V p = split_pair(v[r], bpart[r], w32(r), wtau);
-    ptile_store(ptile, k * ppitch + t, p.x);
-    ptile_store(ptile, (M - k) * ppitch + t, p.y);
+    st.put(k, t, p.x);
+    st.put(M - k, t, p.y);
   }
   if (s == 0) {
     const V p = split_pair(v[8], v[8], w32(8), wtau);
-    ptile_store(ptile, (M / 2) * ppitch + t, p.x);
+    st.put(M / 2, t, p.x);
   }
+}
+template <typename V>
+MMF_HD void ph_split_regs512(const V (&v)[16], const V (&bpart)[8], float* ptile, int ppitch, int t, int s,
+                             typename CxTraits<V>::Tw wtau) {
+  ph_split_regs512_to(v, bpart, TileRows{ptile, ppitch}, t, s, wtau);
 }
 
 // ---- mel projection of one frame column from the power tile, for bands
@@ -403,6 +442,54 @@ MMF_HD void mel_column(const float* pcol, int ppitch, const int* seg_start, cons
     }
     if (j > m0) emit(j - 1, up_prev + acc_dn);
     up_prev = acc_up;
+  }
+}
+
+// ---- mel projection, grouped form (TilePairs layout).  The two-slope bank is cut into segments as
+// above; segment j is covered by n_j groups of four consecutive bins starting at bin 4*g0_j, with the
+// falling / rising weights of the four bins stored densely (zero outside the segment), so that every
+// irregularity of the filterbank sits in the weights and the loop body is uniform:
+//   two 64-bit loads (bins 4g, 4g+1 | 4g+2, 4g+3 of this lane's frame), two broadcast 128-bit loads
+//   (4 falling, 4 rising weights), four packed FFMA2 -- 8 multiply-adds in 8 instructions.
+// segtab[j] = (g0_j, first weight group of segment j) gives a worker its starting point; from there the
+// walk is incremental: segstep[j] = (n_j, pointer step into the tile before segment j, in pk units:
+// -2*pp when segment j starts inside the last group of segment j-1, else 0) -- one 64-bit load per segment and
+// no address is ever rebuilt.  w4[2*i] = falling weights of weight group i as two pk, w4[2*i+1] = rising weights.
+// pcol = the lane's column of the tile (pk units), pp = pk per bin-pair row.
+struct alignas(16) pk2 {
+  pk a, b;
+};
+template <typename Emit>
+MMF_HD void mel_groups(const pk* pcol, int pp, const int2* segtab, const int2* segstep, const pk2* w4, int m0, int m1,
+                       Emit emit) {
+  float up_prev = 0.0f;
+  const int2 e0 = segtab[m0];
+  const pk* p = pcol + (size_t)(2 * e0.x) * pp;
+  const pk2* w = w4 + 2 * e0.y;
+  const int2* st = segstep + m0;
+  const int pp2 = 2 * pp;
+  int n = st->x;  // the first segment starts at its own absolute position: no step
+#pragma unroll 1
+  for (int j = m0; j <= m1; ++j) {
+    ++st;
+    const int2 nx = *st;  // next segment's (count, step), fetched ahead of its use
+    pk d0 = pmake(0.0f, 0.0f), d1 = d0, u0 = d0, u1 = d0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      const pk p01 = p[0], p23 = p[pp];
+      const pk2 wd = w[0], wu = w[1];
+      d0 = sfma(p01, wd.a, d0);
+      d1 = sfma(p23, wd.b, d1);
+      u0 = sfma(p01, wu.a, u0);
+      u1 = sfma(p23, wu.b, u1);
+      p += pp2;
+      w += 2;
+    }
+    const pk d = sadd(d0, d1), u = sadd(u0, u1);
+    if (j > m0) emit(j - 1, up_prev + (plo(d) + phi(d)));
+    up_prev = plo(u) + phi(u);
+    n = nx.x;
+    p += nx.y;
   }
 }
 

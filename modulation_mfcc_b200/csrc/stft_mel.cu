@@ -127,7 +127,9 @@ constexpr int kMaxUnits = 16;  // (n-tile, m-tile) units per warp: n_mels <= 512
 // packed FP32 instructions (fft_regs.cuh)
 // THREADS = 256: two CTAs per SM; THREADS = 512: one CTA per SM with twice the warps, for
 // configurations (large n_fft) whose tiles leave room for only one CTA
-template <int NFFT, typename V, int THREADS>
+// MG = true: power tile in the bin-pair layout (TilePairs) and the grouped mel walk (mel_groups);
+// MG = false: [bin][frame] rows, sparse walk or mma.sync mel
+template <int NFFT, typename V, int THREADS, bool MG>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
     stft_mel_kernel(const __grid_constant__ CUtensorMap tmap, const StftArgs p) {
   constexpr int kThreads = THREADS;  // (shadows the file-level default inside the kernel)
@@ -142,7 +144,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
   // ---- shared memory carve-up (mirrors stft_smem_bytes() on the host)
   float* s_span = reinterpret_cast<float*>(smem_raw);                       // [span_bufs][span_alloc]
   float* s_ptile = s_span + p.span_bufs * p.span_alloc;                     // [pt_bufs][F*ppitch]
-  constexpr int FP = (C::F + 7) & ~7;  // bin rows padded to the MMA K tile; the pad rows stay zero
+  // bin rows padded to the MMA K tile (rows layout) / bin-pair rows padded to whole 4-bin groups (pair
+  // layout: ppitch counts 8-byte words); the pad rows stay zero
+  constexpr int FP = MG ? 4 * ((C::F + 3) / 4) : ((C::F + 7) & ~7);
   Xe* s_xb = reinterpret_cast<Xe*>(s_ptile + ((p.pt_bufs * FP * p.ppitch + 3) & ~3));  // [SLOTS][XBUF]
   Tw* s_tw1 = reinterpret_cast<Tw*>(s_xb + SLOTS * C::XSTRIDE);                // [TW1]
   Tw* s_tw2 = s_tw1 + C::TW1;                                               // [TW2]
@@ -153,9 +157,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
   //   s_mb  [kMaxWorkers + 2] band groups   |   s_npair [NT + 1] pair range of each n-tile
   //                                         |   s_tile  [NT] first band | bands << 16 of each n-tile
   //                                         |   s_units [8][kMaxUnits] (n | m << 8) work list per warp
+  // grouped walk: s_mgw [2 * mg_n] float4 weights | s_mgseg [n_mels + 2] int2 | s_mgstep [n_mels + 3] int2 | s_mb
   float2* s_w2 = s_win + C::M;
   int* s_seg = reinterpret_cast<int*>(s_w2 + C::F);
-  int* s_mb = s_seg + ((p.n_mels + 2 + 1) & ~1);
+  int* s_mb = MG ? reinterpret_cast<int*>(s_win + C::M) + 8 * p.mg_n + 2 * (p.n_mels + 2) + 2 * (p.n_mels + 3)
+                 : s_seg + ((p.n_mels + 2 + 1) & ~1);
+  float4* s_mgw = reinterpret_cast<float4*>(s_win + C::M);
+  int2* s_mgseg = reinterpret_cast<int2*>(s_mgw + 2 * p.mg_n);
+  int2* s_mgstep = s_mgseg + (p.n_mels + 2);
   float2* s_bw = s_win + C::M;
   int* s_pk8 = reinterpret_cast<int*>(s_bw + (size_t)p.mma_n_pairs * 32);
   int* s_npair = s_pk8 + p.mma_n_pairs;
@@ -171,7 +180,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 
   for (int i = tid; i < C::TW1; i += kThreads) s_tw1[i] = make_tw<V>(p.tw1[i]);
   for (int i = tid; i < C::TW2; i += kThreads) s_tw2[i] = make_tw<V>(p.tw2[i]);
-  if (p.mel_mma) {
+  if constexpr (MG) {
+    for (int i = tid; i < 2 * p.mg_n; i += kThreads) s_mgw[i] = p.mg_w[i];
+    for (int i = tid; i < p.n_mels + 2; i += kThreads) s_mgseg[i] = p.mg_seg[i];
+    for (int i = tid; i < p.n_mels + 3; i += kThreads) s_mgstep[i] = p.mg_step[i];
+    for (int i = tid; i < kMaxWorkers + 1; i += kThreads) s_mb[i] = p.band_split[i];
+  } else if (p.mel_mma) {
     const int NT = p.mma_n_tiles;
     for (int i = tid; i < NT; i += kThreads) s_tile[i] = p.mma_tile[i];
     for (int i = tid; i < p.mma_n_pairs * 32; i += kThreads) s_bw[i] = p.mma_bw[i];
@@ -247,6 +261,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
     const int g_first = t0 * p.hop - NFFT / 2 - lead;
     const int shift = g_first - (g_first & ~3);
     float* ptile = s_ptile + (size_t)(p.pt_bufs == 2 ? (it & 1) : 0) * FP * p.ppitch;
+    const TilePairs tpairs{ptile, p.ppitch, p.TF >> 1};
+    const TileRows trows{ptile, p.ppitch};
 
     if (p.use_tma) {
       // two span buffers: prefetch the next tile into the other one now (its last readers
@@ -338,7 +354,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
             const V sh = shfl_cx(v[15 - r], src);
             bpart[r] = (tau == 0) ? v[(16 - r) & 15] : sh;
           }
-          ph_split_regs512(v, bpart, ptile, p.ppitch, f, tau, wtau);
+          if constexpr (MG)
+            ph_split_regs512_to(v, bpart, tpairs, f, tau, wtau);
+          else
+            ph_split_regs512_to(v, bpart, trows, f, tau, wtau);
           done = true;
         }
       }
@@ -359,7 +378,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
           fsync();
           ph_z_gather<NFFT, 2>(za, zb, xb, tau);
         }
-        ph_split_pairs<NFFT>(za, zb, ptile, p.ppitch, f, tau, wtau);
+        if constexpr (MG)
+          ph_split_pairs_to<NFFT>(za, zb, tpairs, f, tau, wtau);
+        else
+          ph_split_pairs_to<NFFT>(za, zb, trows, f, tau, wtau);
       }
     }
     __syncthreads();  // power tile complete
@@ -371,10 +393,37 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
       float* dst = p.power + (size_t)clip * C::F * p.T + t0;
       for (int e = tid; e < C::F * p.TF; e += kThreads) {
         const int k = e / p.TF, t = e - k * p.TF;
-        if (t < t_valid) dst[(size_t)k * p.T + t] = ptile[k * p.ppitch + t];
+        if (t < t_valid) dst[(size_t)k * p.T + t] = MG ? tpairs.get(k, t, TR::kFrames == 2) : trows.get(k, t);
       }
     }
-    if (p.logmel != nullptr && p.mel_mma && !(p.debug_skip & 2)) {
+    if constexpr (MG) {
+      if (p.logmel != nullptr && !(p.debug_skip & 2)) {
+        // ---------------- mel phase, grouped walk: lane -> tile column (one frame), worker -> band group
+        const int c = lane & (p.TF - 1);
+        const int half = p.TF >> 1;
+        const int t = TR::kFrames == 2 ? ((c >= half ? c - half : c) << 1) + (c >= half ? 1 : 0) : c;  // frame of column c
+        const int worker = (tid >> 5) * (32 >> tf_shift) + (lane >> tf_shift);
+        const int m0 = s_mb[worker], m1 = s_mb[worker + 1];
+        float mx = -FLT_MAX;
+        if (m0 < m1 && t < t_valid) {
+          float* dst = p.logmel + ((size_t)clip * p.n_mels + m0) * p.T + t0 + t;
+          const float amin = p.amin;
+          const int T = p.T;
+          auto emit = [&](int, float val) {
+            // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is within 1e-6 dB here (x >= amin, never denormal)
+            const float db = 3.01029995663981195f * fast_log2(fmaxf(amin, val));
+            *dst = db;
+            dst += T;
+            mx = fmaxf(mx, db);
+          };
+          mel_groups(reinterpret_cast<const pk*>(ptile) + c, p.ppitch, s_mgseg, s_mgstep, reinterpret_cast<const pk2*>(s_mgw), m0,
+                     m1, emit);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0 && mx > -FLT_MAX) atomicMax(p.clipmax + clip, float_key(mx));
+      }
+    } else if (p.logmel != nullptr && p.mel_mma && !(p.debug_skip & 2)) {
       // ---------------- mel phase on the tensor cores.
       // D[frame][band] = P[frame][bin] * W[bin][band] in 16x8 output tiles.  Only the (n-tile,
       // k-tile) blocks of the filterbank that are not all zero are listed (n-major, built on the
@@ -473,8 +522,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 // host side
 // ---------------------------------------------------------------------------
 
-size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int n_tiles) {
+size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int n_tiles, int mel_groups, int mg_n) {
   const int F = n_fft / 2 + 1;
+  if (mel_groups)
+    return (size_t)mg_n * 32 + (size_t)(n_mels + 2) * 8 + (size_t)(n_mels + 3) * 8 + (size_t)(kMaxWorkers + 2) * 4;
   if (mel_mma)
     return (size_t)n_pairs * 32 * 8 + (size_t)n_pairs * 4 + (size_t)(2 * n_tiles + 1) * 4 + 8 * kMaxUnits * 4;
   return (size_t)F * 8 + (size_t)((n_mels + 2 + 1) & ~1) * 4 + (size_t)(kMaxWorkers + 2) * 4;
@@ -482,10 +533,10 @@ size_t stft_mel_table_bytes(int n_fft, int n_mels, int mel_mma, int n_pairs, int
 
 template <int NFFT>
 static size_t smem_bytes_t(int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed, size_t mel_tab_bytes,
-                           int threads) {
+                           int threads, int mel_groups) {
   using C = FftCfg<NFFT>;
   const int SLOTS = threads / C::TPF;
-  constexpr int FP = (C::F + 7) & ~7;
+  const int FP = mel_groups ? 4 * ((C::F + 3) / 4) : ((C::F + 7) & ~7);
   const size_t tw_bytes = packed ? sizeof(c2) : sizeof(float2);
   size_t b = 0;
   b += (size_t)span_bufs * span_alloc * 4;
@@ -524,23 +575,28 @@ int stft_geometry(int n_fft, int packed, int threads, StftGeometry* g) {
 }
 
 size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int pt_bufs, int packed,
-                       size_t mel_tab_bytes, int threads) {
+                       size_t mel_tab_bytes, int threads, int mel_groups) {
   switch (n_fft) {
-    case 256: return smem_bytes_t<256>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
-    case 512: return smem_bytes_t<512>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
-    case 1024: return smem_bytes_t<1024>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
-    case 2048: return smem_bytes_t<2048>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
-    case 4096: return smem_bytes_t<4096>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads);
+    case 256: return smem_bytes_t<256>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads, mel_groups);
+    case 512: return smem_bytes_t<512>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads, mel_groups);
+    case 1024: return smem_bytes_t<1024>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads, mel_groups);
+    case 2048: return smem_bytes_t<2048>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads, mel_groups);
+    case 4096: return smem_bytes_t<4096>(span_alloc, span_bufs, ppitch, pt_bufs, packed, mel_tab_bytes, threads, mel_groups);
     default: return 0;
   }
 }
 
-template <int NFFT, typename V, int THREADS>
-static cudaError_t launch_v(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
-  auto kfn = stft_mel_kernel<NFFT, V, THREADS>;
+template <int NFFT, typename V, int THREADS, bool MG>
+static cudaError_t launch_m(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
+  auto kfn = stft_mel_kernel<NFFT, V, THREADS, MG>;
   MMF_SMEM_ONCE(kfn, 227 * 1024);
   kfn<<<grid, THREADS, smem, st>>>(tmap, a);
   return cudaGetLastError();
+}
+template <int NFFT, typename V, int THREADS>
+static cudaError_t launch_v(const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem, cudaStream_t st) {
+  if (a.mel_groups) return launch_m<NFFT, V, THREADS, true>(tmap, a, grid, smem, st);
+  return launch_m<NFFT, V, THREADS, false>(tmap, a, grid, smem, st);
 }
 
 template <int NFFT>

@@ -160,6 +160,41 @@ extern "C" int emu_mel(const float* power, long T, int F, const int* seg_start, 
   return 0;
 }
 
+// grouped mel walk (mel_groups) over the bin-pair tile layout (TilePairs): the power columns are stored
+// exactly as the split step stores them (two-frame groups: put(k, t, pk) -> columns t/2 and t/2 + half; one-frame
+// groups: put(k, t, float)), then every column is projected and un-permuted like the kernel does
+extern "C" int emu_mel_groups(const float* power, long T, int F, const int* segtab, const int* segstep, const float* w,
+                              int n_mels, int bands_per_worker, int tf, int two_frames, float* mel_out) {
+  const int pp = tf + 2, half = tf / 2;
+  const int rows = 2 * ((F + 3) / 4);  // bin-pair rows
+  std::vector<float> tile((size_t)rows * pp * 2, 0.0f);
+  for (long t0 = 0; t0 < T; t0 += tf) {
+    std::fill(tile.begin(), tile.end(), 0.0f);
+    TilePairs tp{tile.data(), pp, half};
+    for (int t = 0; t < tf; t += two_frames ? 2 : 1)
+      for (int k = 0; k < F; ++k) {
+        auto P = [&](long tt) { return tt < T ? power[(long)k * T + tt] : 0.0f; };
+        if (two_frames)
+          tp.put(k, t, pmake(P(t0 + t), P(t0 + t + 1)));
+        else
+          tp.put(k, t, P(t0 + t));
+      }
+    for (int c = 0; c < tf; ++c) {
+      const int t = two_frames ? ((c >= half ? c - half : c) << 1) + (c >= half ? 1 : 0) : c;
+      if (t0 + t >= T) continue;
+      for (int k = 0; k < F; ++k)
+        if (tp.get(k, t, two_frames != 0) != power[(long)k * T + t0 + t]) return -2;
+      for (int m0 = 0; m0 < n_mels; m0 += bands_per_worker) {
+        const int m1 = m0 + bands_per_worker < n_mels ? m0 + bands_per_worker : n_mels;
+        mel_groups(reinterpret_cast<const pk*>(tile.data()) + c, pp, reinterpret_cast<const int2*>(segtab),
+                   reinterpret_cast<const int2*>(segstep), reinterpret_cast<const pk2*>(w), m0, m1,
+                   [&](int m, float v) { mel_out[(long)m * T + t0 + t] = v; });
+      }
+    }
+  }
+  return 0;
+}
+
 // raw 16/8-point DFT checks
 extern "C" void emu_dft16(const float* in, float* out) {
   float2 v[16];

@@ -252,6 +252,8 @@ def emu():
     fp = ctypes.POINTER(ctypes.c_float)
     lib.emu_stft_power.argtypes = [fp, ctypes.c_long, ctypes.c_int, ctypes.c_int, fp, fp, ctypes.c_long, ctypes.c_int]
     lib.emu_mel.argtypes = [fp, ctypes.c_long, ctypes.c_int, ctypes.POINTER(ctypes.c_int), fp, ctypes.c_int, ctypes.c_int, fp]
+    lib.emu_mel_groups.argtypes = [fp, ctypes.c_long, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), fp,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
     return lib
 
 
@@ -311,6 +313,48 @@ def test_emulated_sparse_mel_equals_dense(emu, cfg, bpw):
     emu.emu_mel(_p(P), 7, cfg.n_bins, seg_start.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(w2), cfg.n_mels, bpw, _p(out))
     ref = mel.astype(np.float64) @ P.astype(np.float64)
     assert np.max(np.abs(out - ref)) <= 2e-6 * max(1.0, np.abs(ref).max())
+
+
+def _mel_groups(cfg, pp):
+    """Python restatement of host_mel_groups() (csrc/host_tables.cpp) for the emulator test."""
+    mel, seg_start, w2 = _sparse_mel(cfg)
+    F = cfg.n_bins
+    segtab, segstep, w = [], [], []
+    pos = 0
+    for j in range(cfg.n_mels + 2):
+        a = int(seg_start[j])
+        b = int(seg_start[j + 1]) if j <= cfg.n_mels else a
+        g0 = a // 4
+        g1 = (b + 3) // 4 if b > a else g0
+        segtab.append((g0, len(w) // 8))
+        segstep.append((g1 - g0, (g0 - pos) * 2 * pp if j else 0))
+        pos = g1
+        for g in range(g0, g1):
+            ks = [4 * g + i for i in range(4)]
+            w += [float(w2[k, 0]) if a <= k < b and k < F else 0.0 for k in ks]
+            w += [float(w2[k, 1]) if a <= k < b and k < F else 0.0 for k in ks]
+    segstep.append((0, 0))
+    return mel, np.array(segtab, np.int32), np.array(segstep, np.int32), np.array(w, np.float32)
+
+
+@pytest.mark.parametrize("cfg,bpw,tf,two", [(mm.MfccConfig(16000, 512, 400, 160, 40, 13, 0.0, 8000.0), 5, 32, 1),
+                                            (mm.MfccConfig(10000, 512, 250, 50, 128, 13, 100.0, 10000.0), 16, 32, 1),
+                                            (mm.MfccConfig(44100, 2048, 1102, 441, 128, 20, 0.0, 22050.0), 7, 8, 1),
+                                            (mm.MfccConfig(8000, 256, 200, 80, 32, 12, 0.0, 4000.0), 4, 32, 0),
+                                            (mm.MfccConfig(16000, 512, 400, 160, 40, 13, 300.0, 7000.0), 40, 16, 1)])
+def test_emulated_grouped_mel_equals_dense(emu, cfg, bpw, tf, two):
+    """The grouped mel walk on the bin-pair power tile (the kernel's default mel phase), run on the CPU from the
+    same __host__ __device__ code: equals the dense filterbank product for every band split and tile shape."""
+    mel, segtab, segstep, w = _mel_groups(cfg, tf + 2)
+    rng = np.random.default_rng(4)
+    T = 45  # ragged last tile
+    P = (rng.random((cfg.n_bins, T)) * 10.0 ** rng.uniform(-6, 3, (cfg.n_bins, 1))).astype(np.float32)
+    out = np.zeros((cfg.n_mels, T), np.float32)
+    ip = ctypes.POINTER(ctypes.c_int)
+    rc = emu.emu_mel_groups(_p(P), T, cfg.n_bins, segtab.ctypes.data_as(ip), segstep.ctypes.data_as(ip), _p(w), cfg.n_mels, bpw, tf, two, _p(out))
+    assert rc == 0
+    ref = mel.astype(np.float64) @ P.astype(np.float64)
+    assert np.max(np.abs(out - ref) / np.maximum(ref, 1e-30)) <= 2e-6
 
 
 def test_operand_split_accuracy_study():
