@@ -42,6 +42,23 @@ WORKLOAD = (
 )
 
 
+def config_dict(T: int = 1001) -> dict:
+    """The workload description printed by BOTH arms (identical keys and values)."""
+    return {
+        "workload": WORKLOAD,
+        "clips_per_gpu_per_step": CLIPS,
+        "samples_per_clip": N_SAMPLES,
+        "frames_per_clip": T,
+        "sample_rate": SR,
+        "n_fft": PARAMS["n_fft"],
+        "win_length": int(PARAMS["winLen"] * SR),
+        "hop_length": int(PARAMS["tStep"] * SR),
+        "n_mels": PARAMS["n_mels"],
+        "n_mfcc": PARAMS["n_mfcc"],
+        "l2": "inputs are 655 MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
+    }
+
+
 # --------------------------------------------------------------------------- CPU arm
 
 
@@ -115,7 +132,8 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_step": n_clips, "note": "CPU arm: the numpy/scipy restatement of the reference path (the reference itself cannot be installed offline: DESIGN.md section 2)"},
+        "config": config_dict(),
+        "notes": {"arm": "CPU arm: the numpy/scipy restatement of the reference path, pinned bit for bit to the reference's own script/mfcc.py + calc.py (tests/test_reference_pin.py); librosa itself cannot be installed offline (DESIGN.md section 2)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -182,6 +200,46 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------- GPU arm
 
 
+def _bind_to_gpu_numa_node(index: int):
+    """Best effort: run this rank on the CPUs next to its GPU, so that the pinned staging buffers it allocates
+    afterwards are NUMA-local to the GPU's PCIe root (first-touch policy)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+class PowerSampler(ClockSampler):
+    """ClockSampler that also records board power."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(index, period)
+        self.power = []
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -194,6 +252,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    numa_cpus = _bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -204,24 +263,35 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     lib = mm.lib()
     fx = mm.FeatureExtractor(SR, device=local, flags=int(os.environ.get("MMF_FLAGS", "0")), **PARAMS)
     plan, prm = fx.plan, fx.prm
     pcm = mm.synth_batch_device(CLIPS, N_SAMPLES, SR, seed=1234 + rank, device=dev)
     T = plan.num_frames(N_SAMPLES)
     Lw, Hw, nfft, bins = fx.modspec_geometry(T)
-    # the only collective (north_star): ONE final gather of the per-clip feature of every step, issued
-    # after the last step and inside the timed region.  Each step parks its totChange in a slice of
-    # `local_feats`; nothing communicates while the persistent kernels own the SMs.
-    local_feats = gathered = None
+    n_win = 1 + (T - Lw) // Hw
+    # Per-clip feature gather (north_star: the only cross-GPU traffic).  Every step's MFCC-change curves
+    # [1024, T] f64 go to EVERY rank through NVLink peer memory, pushed by the copy engines right after the
+    # step while the SMs run the next one (modulation_mfcc_b200.shard.PeerGather); the timed region ends only
+    # when all ranks hold all steps' curves.  Rank-major rows: rank r owns [r*R, (r+1)*R), R = n_keep * CLIPS.
+    n_keep = max(args.steps, args.warmup, 3)
+    gather = None
     if world > 1:
-        n_keep = max(args.steps, args.warmup, 3)
-        local_feats = torch.empty((n_keep, CLIPS, T), device=dev, dtype=torch.float64)
-        gathered = torch.empty((world, n_keep, CLIPS, T), device=dev, dtype=torch.float64)
+        gather = mm.PeerGather(world * n_keep * CLIPS, (T,), torch.float64, dev,
+                               force_collective=bool(int(os.environ.get("MMF_BENCH_NCCL_GATHER", "0"))))
+        _GATHER_MODE["mode"] = ("copy-engine pushes over NVLink peer memory after each step, torch symmetric memory"
+                                if gather.mode == "peer" else "one in-place NCCL all_gather_into_tensor at the end: " + gather.mode)
 
-    k1_events = []
+    k1_events, k6_events = [], []
 
-    def step(record: bool):
+    def step(record: bool, slot: int):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -230,24 +300,21 @@ def run_b200(args):
             e1.record()
             k1_events.append((e0, e1))
         res = plan.change_from_logmel(lm, cmax, prm, clamp_in_place=False)  # clamp+DCT+delta, IIR, derivative+norm, IIR
+        if record:
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
         mag, band = plan.modspec(res["mfcc"], Lw, Hw, nfft, bins)
-        if world > 1:
-            local_feats[step.count % local_feats.shape[0]].copy_(res["totChange"])
-            step.count += 1
+        if record:
+            e3.record()
+            k6_events.append((e2, e3))
+        if gather is not None:
+            gather.push(res["totChange"], (rank * n_keep + slot % n_keep) * CLIPS)
         return res, mag, band
 
-    step.count = 0
-
-    def final_gather(n_steps):
-        if world > 1:
-            n = min(n_steps, local_feats.shape[0])
-            dist.all_gather_into_tensor(gathered[:, :n].contiguous() if n < local_feats.shape[0] else gathered,
-                                        local_feats[:n].contiguous() if n < local_feats.shape[0] else local_feats)
-
-    for _ in range(max(args.warmup, 3)):
-        step(False)
-    final_gather(max(args.warmup, 3))
-    step.count = 0
+    for i in range(max(args.warmup, 3)):
+        step(False, i)
+    if gather is not None:
+        gather.finish()  # same sizes and paths as the timed region
     torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local)
@@ -256,21 +323,59 @@ def run_b200(args):
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        step(True)
-    final_gather(args.steps)  # the gather of all steps' features lands before the clock stops
+    for i in range(args.steps):
+        last = step(True, i)
+    gathered = None
+    if gather is not None:
+        gathered = gather.finish()  # every rank's curves of every step have landed before the clock stops
     ev1.record()
     torch.cuda.synchronize()
     barrier()
     launches = int(lib.mmf_launch_count(0))
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     k1_ms = [a.elapsed_time(b) for a, b in k1_events]
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    k6_ms = [a.elapsed_time(b) for a, b in k6_events]
     ms_step = ms_total / args.steps
     value = world * CLIPS * SECONDS / (ms_step * 1e-3)
+    clocks = sampler.stop()
+    gather_ok = None
+    if gather is not None:
+        # the gathered block of this rank's last step must be the curve it computed
+        row0 = (rank * n_keep + (args.steps - 1) % n_keep) * CLIPS
+        gather_ok = bool(torch.equal(gathered[row0 : row0 + CLIPS], last[0]["totChange"]))
+        peer = (rank + 1) % world
+        gather_ok = gather_ok and bool(torch.isfinite(gathered[(peer * n_keep) * CLIPS : (peer * n_keep + 1) * CLIPS]).all())
+
+    # ---- sustained: the same step back to back for >= 2 s (clocks and power settle; MEASURED_PEAKS' sustained figure)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(200, int(2.2 / (ms_step * 1e-3)))
+        ps = PowerSampler(local)
+        torch.cuda.synchronize()
+        barrier()
+        ps.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_sus):
+            step(False, i)
+        if gather is not None:
+            gather.finish()
+        s1.record()
+        torch.cuda.synchronize()
+        sus_ms = max_over_ranks(s0.elapsed_time(s1))
+        pc = ps.stop()
+        barrier()
+        sustained = {
+            "value": world * CLIPS * SECONDS * n_sus / (sus_ms * 1e-3),
+            "unit": UNIT,
+            "steps": n_sus,
+            "seconds": sus_ms * 1e-3,
+            "ms_per_step": sus_ms / n_sus,
+            "sm_mhz": pc["sm_mhz"],
+            "sm_max_mhz": pc["sm_max_mhz"],
+            "power_w_median": statistics.median(ps.power) if ps.power else None,
+            "power_w_max": max(ps.power) if ps.power else None,
+        }
 
     # ---- end to end through the host-buffer C-ABI call (pinned host PCM in, host features out)
     pcm_host_t = torch.empty((CLIPS, N_SAMPLES), dtype=torch.float32, pin_memory=True)
@@ -278,7 +383,6 @@ def run_b200(args):
     torch.cuda.synchronize()
     pcm_host = pcm_host_t.numpy()
     want = ("totChange", "mfcc", "delta", "modspec", "band_energy")
-    n_win = 1 + (T - Lw) // Hw
     shapes = {
         "totChange": ((CLIPS, T), torch.float64),
         "mfcc": ((CLIPS, 13, T), torch.float32),
@@ -295,14 +399,27 @@ def run_b200(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         fx.host_call(pcm_host, want=want, out=out)  # synchronous: returns when the results are in host memory
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    clocks = sampler.stop()
     e2e_value = world * CLIPS * SECONDS * e2e_steps / e2e_s
+    # outside the timed region: what the e2e call (14 chunks over two streams) left in host memory must be
+    # bit-identical to the device-resident step
+    dev_res = {"totChange": last[0]["totChange"], "mfcc": last[0]["mfcc"], "delta": last[0]["delta"], "modspec": last[1], "band_energy": last[2]}
+    e2e_verified = all(bool(torch.equal(torch.from_numpy(out[k]), dev_res[k].cpu())) for k in want)
+    # raw H2D ceiling of this host for the same pinned buffer, all ranks copying at once
+    h2d_buf = torch.empty_like(pcm)
+    for _ in range(2):
+        h2d_buf.copy_(pcm_host_t, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        h2d_buf.copy_(pcm_host_t, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    h2d_gbs = world * 5 * CLIPS * N_SAMPLES * 4 / h2d_s / 1e9
+    del h2d_buf
     # extra (not the contract's `e2e`): the same call fed with 16-bit PCM as it sits in a WAV file --
     # half the H2D bytes, scaled to float32 on the device; inputs are the float batch quantised to int16
     pcm16_t = torch.empty((CLIPS, N_SAMPLES), dtype=torch.int16, pin_memory=True)
@@ -315,15 +432,67 @@ def run_b200(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         fx.host_call(pcm16_host, want=want, out=out)
-    e16_s = time.perf_counter() - t0
-    te = torch.tensor([e16_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e16_s = float(te.item())
+    e16_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e16_value = world * CLIPS * SECONDS * e2e_steps / e16_s
     h2d = CLIPS * N_SAMPLES * 4
     d2h = sum(int(np.prod(s)) * (8 if d == torch.float64 else 4) for s, d in shapes.values())
+    del pcm_host_t, pcm16_t, pinned, out
+
+    # ---- BASELINE configs[4]: the 100k-clip corpus, block-partitioned over the ranks (CorpusRunner)
+    cfg5 = None
+    if not args.no_cfg5:
+        n_corpus = args.corpus_clips
+        lo, hi = mm.shard_range(n_corpus, rank, world)
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        need = (hi - lo) * N_SAMPLES * 4 + n_corpus * T * 8 + (6 << 30)
+        gather = gathered = last = None
+        torch.cuda.empty_cache()
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        ok_mem = max_over_ranks(0.0 if need <= free_b else 1.0) == 0.0
+        if ok_mem:
+            shard = torch.empty((hi - lo, N_SAMPLES), device=dev, dtype=torch.float32)
+            for b0 in range(0, hi - lo, CLIPS):  # stands in for the loader: not timed
+                nb = min(CLIPS, hi - lo - b0)
+                shard[b0 : b0 + nb] = mm.synth_batch_device(nb, N_SAMPLES, SR, seed=99 + lo + b0, device=dev)
+            g5 = mm.PeerGather(n_corpus, (T,), torch.float64, dev) if world > 1 else None
+            runner = mm.CorpusRunner(fx, n_corpus, N_SAMPLES, batch=CLIPS, rank=rank, world=world, gather=g5)
+            # warm-up pass over the first batches (kernel attributes, allocator pools, peer mappings)
+            warm = mm.CorpusRunner(fx, min(n_corpus, 2 * CLIPS * world), N_SAMPLES, batch=CLIPS, rank=rank, world=world)
+            warm.run(shard[: warm.hi - warm.lo])
+            torch.cuda.synchronize()
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            lib.mmf_launch_count(1)
+            c0.record()
+            runner.run(shard)
+            full = runner.finish()
+            c1.record()
+            torch.cuda.synchronize()
+            c_launch = int(lib.mmf_launch_count(0))
+            c_ms = max_over_ranks(c0.elapsed_time(c1))
+            barrier()
+            # parity sample: one clip of this rank's shard against the single-clip call
+            ref1 = fx(shard[:1], want_logmel=False)["totChange"][0]
+            row = full[lo] if world > 1 else full[0]
+            cfg5 = {
+                "workload": f"BASELINE configs[4]: {n_corpus} x 10 s 16 kHz clips, contiguous block partition over {world} GPU(s), batches of {CLIPS}; per-clip MFCC-change curves gathered on every rank, modulation band energies kept per shard",
+                "clips": n_corpus,
+                "clips_on_rank0": hi - lo,
+                "ms": c_ms,
+                "value": n_corpus * SECONDS / (c_ms * 1e-3),
+                "unit": UNIT,
+                "us_per_clip_per_gpu": c_ms * 1e3 / max(1, (n_corpus + world - 1) // world),
+                "gather": (g5.mode if g5 is not None else "none"),
+                "gathered_shape": list(full.shape),
+                "gathered_finite": bool(torch.isfinite(full).all()),
+                "sample_matches_single_clip_call": bool(torch.equal(row, ref1)),
+                "gpu_launches": c_launch,
+                "scaling": "strong (fixed corpus)",
+            }
+            del shard, full, runner, warm, g5
+        else:
+            cfg5 = {"skipped": f"needs {need / 2**30:.0f} GiB of HBM on the largest shard, {free_b / 2**30:.0f} GiB free"}
 
     if rank != 0:
         if world > 1:
@@ -342,12 +511,20 @@ def run_b200(args):
     alg_bytes = CLIPS * (4 * N_SAMPLES + 4 * PARAMS["n_mels"] * T)
     k1 = statistics.mean(k1_ms)
     achieved = alg_bytes / (k1 * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_src = None
     try:
         with open(os.path.join(ROOT, "profiles", "stft_mel_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "static: " + tj.get("source", "ncu --set full capture under profiles/ (not measured in this run)")
     except Exception:
         pass
+    # K6 (modulation spectrum): MFCC rows in + magnitudes + band energies out
+    k6 = statistics.mean(k6_ms)
+    k6_bytes = CLIPS * (4 * 13 * T + 4 * 13 * n_win * (nfft // 2 + 1) + 4 * n_win * len(bins))
+    # whole step: compulsory bytes of the fused path (SURVEY section 8d "end-to-end compulsory" + log-mel is
+    # NOT an output here): PCM in, MFCC + delta, modulation magnitudes + band energies, totChange f64 out
+    step_bytes = CLIPS * (4 * N_SAMPLES + 8 * 13 * T + 4 * 13 * n_win * (nfft // 2 + 1) + 4 * n_win * len(bins) + 8 * T)
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -374,13 +551,12 @@ def run_b200(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {
-            "workload": WORKLOAD,
-            "clips_per_gpu": CLIPS,
-            "frames_per_clip": T,
-            "l2": "inputs are 655 MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
-            "collective": "one final all_gather_into_tensor of every step's totChange, inside the timed region" if world > 1 else "none",
+        "config": config_dict(T),
+        "notes": {
+            "collective": (f"per-clip MFCC-change curves of every step land on every rank inside the timed region ({gather_mode(world)})" if world > 1 else "none"),
+            "gather_verified": gather_ok,
             "fp64_stages": "zero-phase Butterworth and derivative/norm run in f64; the modulation spectrum is a tcgen05 GEMM (fp16 operand pairs, f32 accumulate)",
+            "numa_cpus_bound": numa_cpus,
         },
         "clocks": clocks,
         "e2e": {
@@ -390,6 +566,9 @@ def run_b200(args):
             "d2h_bytes_per_step": d2h,
             "steps": e2e_steps,
             "call": "mmf_features_host (one C-ABI call per step, pinned host buffers)",
+            "verified_bit_identical_to_device_path": e2e_verified,
+            "h2d_ceiling_gbs_all_ranks": h2d_gbs,
+            "h2d_achieved_gbs_all_ranks": world * e2e_steps * h2d / e2e_s / 1e9,
         },
         "e2e_pcm16": {
             "value": e2e16_value,
@@ -408,16 +587,45 @@ def run_b200(args):
             "unit": "GB/s",
             "frac": achieved / hbm_peak,
             "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes,
             "kernel_ms": k1,
             "kernel_share_of_step": k1 / ms_step,
         },
+        "roofline_k6": {
+            "kernel": "modspec_tc_kernel<128, 7> (modulation spectrum, tcgen05 GEMM)",
+            "bound": "hbm",
+            "achieved": k6_bytes / (k6 * 1e-3) / 1e9,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": k6_bytes / (k6 * 1e-3) / 1e9 / hbm_peak,
+            "algorithmic_bytes_per_launch": k6_bytes,
+            "kernel_ms": k6,
+        },
+        "roofline_step": {
+            "what": "whole step, compulsory bytes (PCM in; MFCC, delta, modulation magnitudes, band energies, totChange out)",
+            "bound": "hbm",
+            "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+            "algorithmic_bytes_per_step": step_bytes,
+        },
+        "sustained": sustained,
+        "cfg5": cfg5,
         "cpu_baseline": cpu,
     }
     if world > 1:
         dist.destroy_process_group()
     return line
+
+
+_GATHER_MODE = {"mode": "none"}
+
+
+def gather_mode(world):
+    return _GATHER_MODE["mode"]
 
 
 class _StdoutToStderr:
@@ -444,6 +652,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained-clock leg")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the 100k-clip corpus leg (BASELINE configs[4])")
+    ap.add_argument("--corpus-clips", type=int, default=100_000)
     args = ap.parse_args()
     with _StdoutToStderr():
         line = run_reference(args) if args.impl == "reference" else run_b200(args)

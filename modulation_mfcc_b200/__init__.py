@@ -32,7 +32,8 @@ from .api import (  # noqa: F401
     mfcc_features_batch,
     modspec_sizes,
 )
-from .shard import gather_features, shard_range, shard_sizes  # noqa: F401
+from .shard import PeerGather, gather_features, shard_range, shard_sizes  # noqa: F401
+from .corpus import CorpusRunner  # noqa: F401
 from .synth import synth_batch, synth_batch_device, synth_clip  # noqa: F401
 
 __version__ = "0.1.0"
