@@ -209,8 +209,9 @@ int mmf_features_host_pcm16(mmf_plan* plan, const int16_t* pcm16_host, int64_t n
                             float* band_host);
 
 /* Hilbert amplitude envelope |scipy.signal.hilbert(x)| of each row (script/calc.py:284-286, method 'Hilb'),
- * any length n <= 2^24: evaluated as the circular convolution with the discrete Hilbert kernel that scipy's
- * FFT formulation is equivalent to (n^2 FMAs; about a millisecond for a 10 s clip at 16 kHz). */
+ * any length n <= 2^26 (an hour at 16 kHz): O(n log n) -- the length-n transforms scipy runs are evaluated as
+ * Bluestein chirp transforms over a power-of-two FFT in float64; signals of at most 4096 samples use the
+ * equivalent direct circular convolution with the discrete Hilbert kernel. */
 int mmf_hilbert_envelope(mmf_plan* plan, const float* x_dev, int64_t n_clips, int64_t n, int64_t x_stride,
                          float* amp_dev, int64_t amp_stride, void* stream);
 

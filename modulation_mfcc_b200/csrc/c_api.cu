@@ -32,8 +32,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 
 static int validate_cfg(const mmf_config* c) {
   if (!c) return fail(MMF_ERR_INVALID, "config is NULL");
-  if (c->n_fft < 256 || c->n_fft > 4096 || (c->n_fft & (c->n_fft - 1)))
-    return fail(MMF_ERR_UNSUPPORTED, "n_fft must be a power of two in [256, 4096]");
+  if (c->n_fft < 16 || c->n_fft > 4096) return fail(MMF_ERR_UNSUPPORTED, "n_fft must be in [16, 4096]");
   if (c->win_length < 1 || c->win_length > c->n_fft)
     return fail(MMF_ERR_INVALID, "Target size (n_fft) must be at least input size (win_length)");
   if (c->hop_length < 1) return fail(MMF_ERR_INVALID, "hop_length must be a positive integer");
@@ -275,8 +274,12 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
   p->cfg = *cfg;
   p->F = cfg->n_fft / 2 + 1;
   p->sm_count = prop.multiProcessorCount;
-  p->packed = (stft_packed_supported(cfg->n_fft) && !(cfg->flags & MMF_FLAG_SCALAR_FFT)) ? 1 : 0;
-  stft_geometry(cfg->n_fft, p->packed, 256, &p->geo);
+  // the register FFT covers powers of two in [256, 4096]; every other n_fft librosa accepts goes through the
+  // FP32 matrix-product DFT (dft_generic.cu)
+  p->generic = (cfg->n_fft < 256 || (cfg->n_fft & (cfg->n_fft - 1))) ? 1 : 0;
+  p->packed = (!p->generic && stft_packed_supported(cfg->n_fft) && !(cfg->flags & MMF_FLAG_SCALAR_FFT)) ? 1 : 0;
+  p->geo = StftGeometry{};
+  if (!p->generic) stft_geometry(cfg->n_fft, p->packed, 256, &p->geo);
   p->lead = cfg->preemph != 0.0f ? 2 : 0;
 
   // ---- constant tables
@@ -290,6 +293,29 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     return fail(MMF_ERR_UNSUPPORTED, "mel filterbank is not a two-slope (triangular) bank");
   }
   host_dct(cfg->n_mfcc, cfg->n_mels, dct);
+  if (p->generic) {
+    std::vector<float> tab;
+    dft_generic_table(cfg->n_fft, window, tab, &p->dft_ld);
+    p->nc_pad = cfg->n_mfcc <= 16 ? 16 : (cfg->n_mfcc <= 32 ? 32 : (cfg->n_mfcc <= 64 ? 64 : 128));
+    std::vector<float> dct_pad((size_t)cfg->n_mels * p->nc_pad, 0.0f);
+    for (int k = 0; k < cfg->n_mfcc; ++k)
+      for (int m = 0; m < cfg->n_mels; ++m) dct_pad[(size_t)m * p->nc_pad + k] = dct[(size_t)k * cfg->n_mels + m];
+    std::vector<float2> w2(p->F);
+    for (int k = 0; k < p->F; ++k) w2[k] = make_float2(sp.w2[2 * k], sp.w2[2 * k + 1]);
+    std::vector<float4> dct_bfrag;
+    mfcc_mma_bfrag(dct.data(), cfg->n_mfcc, cfg->n_mels, dct_bfrag);
+    cudaError_t e;
+    if ((e = upload(&p->d_dft_tab, tab)) != cudaSuccess || (e = upload(&p->d_window, window)) != cudaSuccess ||
+        (e = upload(&p->d_seg, sp.seg_start)) != cudaSuccess || (e = upload(&p->d_w2, w2)) != cudaSuccess ||
+        (e = upload(&p->d_dct, dct_pad)) != cudaSuccess || (e = upload(&p->d_dct_bfrag, dct_bfrag)) != cudaSuccess) {
+      mmf_plan_destroy(p);
+      return cuda_fail(e, "uploading plan constants (generic n_fft)");
+    }
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&p->events[i], cudaEventDisableTiming);
+    *out = p;
+    return MMF_OK;
+  }
   // grouped mel walk on the bin-pair power tile: the default; MMF_FLAG_MEL_WALK / MMF_FLAG_MMA_MEL select
   // the [bin][frame] tile with the sparse walk / the mma.sync projection
   MelGroups mg;
@@ -593,6 +619,7 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaSetDevice(p->cfg.device);
   cudaDeviceSynchronize();
   cudaFree(p->d_window);
+  cudaFree(p->d_dft_tab);
   cudaFree(p->d_dct_tc);
   cudaFree(p->d_tc_btab);
   cudaFree(p->d_tc_tw);
@@ -646,6 +673,32 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   if (T > 0x7fffffff || n_samples + c.n_fft > 0x7fffffffLL)
     return fail(MMF_ERR_UNSUPPORTED, "clip longer than 2^31 samples");
   MMF_CUDA(cudaSetDevice(c.device));
+
+  if (p->generic) {
+    // FP32 matrix-product DFT -> power spectrum in HBM (the caller's buffer, or stream-ordered scratch in clip
+    // chunks of <= 1 GiB) -> sparse mel walk + log, one frame per thread
+    if (clipmax) {
+      cudaError_t e = fill_i32_launch(clipmax, n_clips, (int)0x80800000, st);
+      if (e != cudaSuccess) return cuda_fail(e, "clipmax init");
+    }
+    const size_t per_clip = (size_t)p->F * T * 4;
+    const int64_t chunk = power ? n_clips : std::max<int64_t>(1, std::min<int64_t>(n_clips, ((size_t)1 << 30) / per_clip));
+    float* scratch = nullptr;
+    if (!power) MMF_CUDA(cudaMallocAsync((void**)&scratch, (size_t)chunk * per_clip, st));
+    cudaError_t e = cudaSuccess;
+    for (int64_t c0 = 0; c0 < n_clips && e == cudaSuccess; c0 += chunk) {
+      const int64_t nc = std::min<int64_t>(chunk, n_clips - c0);
+      float* pw = power ? power + (size_t)c0 * p->F * T : scratch;
+      e = dft_generic_power_launch(pcm + (size_t)c0 * clip_stride, nc, n_samples, clip_stride, (int)T, c.hop_length,
+                                   c.n_fft, c.preemph, p->d_dft_tab, p->dft_ld, pw, st);
+      if (e == cudaSuccess && logmel)
+        e = mel_from_power_launch(pw, nc, p->F, (int)T, c.n_mels, c.amin, p->d_seg, p->d_w2,
+                                  logmel + (size_t)c0 * c.n_mels * T, clipmax + c0, st);
+    }
+    if (scratch) cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return cuda_fail(e, "generic DFT kernels launch");
+    return MMF_OK;
+  }
 
   StftArgs a{};
   a.pcm = pcm;
@@ -1198,10 +1251,16 @@ int mmf_features_host_pcm16(mmf_plan* plan, const int16_t* pcm16_host, int64_t n
 int mmf_hilbert_envelope(mmf_plan* plan, const float* x_dev, int64_t n_clips, int64_t n, int64_t x_stride,
                          float* amp_dev, int64_t amp_stride, void* stream) {
   if (!plan || !x_dev || !amp_dev) return fail(MMF_ERR_INVALID, "NULL argument");
-  if (n_clips < 1 || n < 1 || n > (1L << 24)) return fail(MMF_ERR_UNSUPPORTED, "need 1 <= n <= 2^24 samples");
+  if (n_clips < 1 || n < 1 || n > (1L << 26)) return fail(MMF_ERR_UNSUPPORTED, "need 1 <= n <= 2^26 samples");
   MMF_CUDA(cudaSetDevice(plan->cfg.device));
-  cudaError_t e = hilbert_envelope_launch(x_dev, n_clips, n, x_stride, amp_dev, amp_stride, plan->sm_count,
-                                          (cudaStream_t)stream);
+  cudaError_t e;
+  if (n > 4096 && hilbert_fft_supported(n)) {
+    // O(n log n): Bluestein chirp transform over a power-of-two Stockham FFT, float64 (hilbert_fft.cu)
+    e = hilbert_fft_launch(x_dev, n_clips, n, x_stride, amp_dev, amp_stride, (cudaStream_t)stream);
+  } else {
+    // short signals: the equivalent circular convolution with the discrete Hilbert kernel, evaluated directly
+    e = hilbert_envelope_launch(x_dev, n_clips, n, x_stride, amp_dev, amp_stride, plan->sm_count, (cudaStream_t)stream);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "hilbert kernels launch");
   return MMF_OK;
 }

@@ -78,6 +78,15 @@ size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
                             cudaStream_t st);
 
+// ---- generic n_fft (anything but a power of two in [256, 4096]): FP32 matrix-product DFT (dft_generic.cu)
+void dft_generic_table(int n_fft, const std::vector<float>& window, std::vector<float>& tab, int* ld_out);
+cudaError_t dft_generic_power_launch(const float* pcm, long n_clips, long n_samples, long clip_stride, int T, int hop,
+                                     int n_fft, float preemph, const float* btab, int ld_b, float* power,
+                                     cudaStream_t st);
+cudaError_t mel_from_power_launch(const float* power, long n_clips, int F, int T, int n_mels, float amin,
+                                  const int* seg_start, const float2* w2, float* logmel, int* clipmax,
+                                  cudaStream_t st);
+
 // ---- 512-point frames on the tcgen05 tensor cores (tc_fft.cu, MMF_FLAG_TC_FFT)
 void tc_fft_tables(std::vector<uint16_t>& btab, std::vector<float>& tw);
 bool tc_fft_supported(int n_fft, int hop, float preemph);
@@ -165,6 +174,9 @@ cudaError_t rms_launch(const float* pcm, long n_clips, long n, long stride, int 
 cudaError_t fill_i32_launch(int* p, long n, int v, cudaStream_t st);
 cudaError_t hilbert_envelope_launch(const float* x, long n_clips, long n, long stride, float* amp, long amp_stride,
                                     int sm_count, cudaStream_t st);
+bool hilbert_fft_supported(long n);
+cudaError_t hilbert_fft_launch(const float* x, long n_clips, long n, long stride, float* amp, long amp_stride,
+                               cudaStream_t st);
 cudaError_t find_peaks_launch(const double* x, long rows, long T, long stride, int minima, int max_peaks, int* idx,
                               int* count, cudaStream_t st);
 cudaError_t pcm16_to_f32_launch(const int16_t* x, long n, float* y, cudaStream_t st);
@@ -219,6 +231,10 @@ struct mmf_plan {
   // tile geometry
   int TF, ppitch, pt_bufs, span_bufs, ctas_per_sm, lead, packed, mel_mma, threads = 256;
   size_t smem;
+  // generic n_fft: FP32 matrix-product DFT instead of the register FFT
+  int generic = 0;
+  float* d_dft_tab = nullptr;
+  int dft_ld = 0;
   // device constants
   float* d_window = nullptr;
   float2* d_tw1 = nullptr;

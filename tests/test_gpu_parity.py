@@ -162,6 +162,45 @@ def test_mfcc_tensor_core_variant(name, cuda_device):
         assert np.max(np.abs(lm[i] - inter["logmel"])) < 4.4e-4  # clamped in place
 
 
+GENERIC_NFFT = {
+    # name: (sr, n_fft, win_length, hop, n_mels, n_mfcc, fmin, fmax, seconds): sizes the register FFT does not cover
+    "nfft400_win_eq": (16000, 400, 400, 160, 40, 13, 0.0, 8000.0, 2.0),
+    "nfft500_gui_rate": (10000, 500, 250, 50, 128, 13, 100.0, 10000.0, 2.0),
+    "nfft401_odd": (16000, 401, 321, 160, 40, 13, 0.0, 8000.0, 1.0),
+    "nfft128_small": (8000, 128, 100, 40, 24, 12, 0.0, 4000.0, 1.0),
+    "nfft1200": (44100, 1200, 1102, 441, 64, 20, 20.0, 22050.0, 1.0),
+    "nfft3000": (48000, 3000, 2400, 480, 80, 13, 0.0, 24000.0, 0.5),
+}
+
+
+@pytest.mark.parametrize("name", list(GENERIC_NFFT))
+def test_generic_n_fft_matrix_product_dft(name, cuda_device):
+    """librosa.stft takes any n_fft (script/mfcc.py:387; the GUI field is free text): everything that is not a
+    power of two in [256, 4096] runs the FP32 matrix-product DFT + the sparse mel walk."""
+    sr, n_fft, win, hop, n_mels, n_mfcc, fmin, fmax, secs = GENERIC_NFFT[name]
+    cfg = mm.MfccConfig(sr, n_fft, win, hop, n_mels, n_mfcc, fmin, fmax)
+    y = synth_batch(50, 3, int(sr * secs), sr)
+    plan = mm.get_plan(cfg)
+    P = plan.stft_power(y).cpu().numpy()
+    for i in range(3):
+        ref = oracle.stft_power(y[i], n_fft, hop, win)
+        assert P[i].shape == ref.shape
+        assert np.max(np.abs(P[i] - ref) / ref.max(axis=0, keepdims=True)) < 1e-5
+    lm, cmax = plan.logmel(y)
+    mf, d = plan.mfcc(lm.clone(), cmax, delta=True)
+    for i in range(3):
+        M, inter, unclamped = _oracle_unclamped(y[i], cfg)
+        assert _mel_rel_err(lm[i].cpu().numpy(), unclamped) < LOGMEL_REL
+        assert np.max(np.abs(mf[i].cpu().numpy() - M)) < ABS_TOL
+        assert np.max(np.abs(d[i].cpu().numpy() - np.gradient(M, axis=1))) < ABS_TOL
+    if name == "nfft500_gui_rate":  # through the reference-facing call
+        kw = dict(KW_GUI)
+        kw["n_fft"] = 500
+        tot, T = mm.get_MFCCS_change(y[0], sr, **kw)
+        rtot, rT = oracle.get_MFCCS_change(y[0], sr, **kw)
+        assert np.array_equal(T, rT) and np.max(np.abs(tot - rtot)) < ABS_TOL
+
+
 def test_clamp_is_active_on_gui_default(cuda_device):
     """fmax above Nyquist leaves empty mel filters at -100 dB, so top_db=80 always clamps."""
     cfg, secs = _cfg("gui_default")
@@ -789,19 +828,36 @@ def test_cuda_path_against_golden_edge_cases(cuda_device):
     assert np.array_equal(T, g["t22_T"]) and np.max(np.abs(tot - g["t22_tot"])) < ABS_TOL
 
 
-@pytest.mark.parametrize("n", [16000, 12345, 4097, 100])
+@pytest.mark.parametrize("n", [160000, 16000, 12345, 4097, 4096, 1000, 100, 441000, 65537])
 def test_hilbert_envelope_matches_scipy(n, cuda_device):
-    """'Hilb' amplitude (script/calc.py:284-286): |scipy.signal.hilbert(x)|, even and odd lengths."""
+    """'Hilb' amplitude (script/calc.py:284-286): |scipy.signal.hilbert(x)| at the signal's own length -- even, odd,
+    prime (65537), 2^k; above 4096 samples through the O(n log n) Bluestein path."""
     x = synth_clip(13, n, 16000)
     plan = mm.get_plan(_cfg("cfg1_16k")[0])
     amp = plan.hilbert_envelope(x).cpu().numpy()
     ref = np.abs(scipy.signal.hilbert(x.astype(np.float64)))
     assert amp.shape == ref.shape
-    assert np.max(np.abs(amp - ref)) < 1e-4
+    assert np.max(np.abs(amp - ref)) < (2e-6 if n > 4096 else 1e-4)
     if n == 16000:
         a, t = mm.calculate_amplitude_envelope(x, 16000, method="Hilb")
         ra, rt = oracle.calculate_amplitude_envelope(x, 16000, method="Hilb")
         assert np.max(np.abs(a - ra)) < 1e-4 and np.array_equal(t, rt)
+
+
+def test_hilbert_envelope_batch_and_one_hour(cuda_device):
+    torch = _torch()
+    plan = mm.get_plan(_cfg("cfg1_16k")[0])
+    xb = synth_batch(70, 3, 30011, 16000)
+    amp = plan.hilbert_envelope(xb).cpu().numpy()
+    for i in range(3):
+        assert np.max(np.abs(amp[i] - np.abs(scipy.signal.hilbert(xb[i].astype(np.float64))))) < 2e-6
+    # one hour at 16 kHz (57.6 M samples): analytic known answer, an amplitude-modulated carrier on an exact bin
+    n = 57_600_000
+    t = torch.arange(n, device=cuda_device, dtype=torch.float64)
+    env = 0.6 + 0.3 * torch.cos(2 * torch.pi * 5.0 * t / n)
+    x = (env * torch.cos(2 * torch.pi * 1_000_000.0 * t / n)).to(torch.float32)
+    got = plan.hilbert_envelope(x)
+    assert float((got.double() - env).abs().max()) < 1e-5
 
 
 def _random_cases(n_cases=28, seed=2026):

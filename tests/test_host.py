@@ -73,9 +73,14 @@ def test_host_tables_equal_oracle(cfg):
 
 def test_config_validation_without_gpu():
     lib = mm.lib()
-    bad = mm.MfccConfig(16000, 500, 400, 160, 40, 13).to_c()
+    bad = mm.MfccConfig(16000, 8192, 400, 160, 40, 13).to_c()
     assert lib.mmf_host_tables(ctypes.byref(bad), None, None, None) == _lib.MMF_ERR_UNSUPPORTED
-    assert b"power of two" in lib.mmf_last_error()
+    assert b"n_fft must be in [16, 4096]" in lib.mmf_last_error()
+    # any n_fft in range is accepted (librosa takes any; non powers of two run the matrix-product DFT)
+    ok = mm.MfccConfig(16000, 500, 400, 160, 40, 13)
+    w, m, d = mm.host_tables(ok)
+    assert w.shape == (500,) and m.shape == (40, 251) and np.allclose(w, oracle.padded_hann(400, 500), atol=1e-7)
+    assert np.max(np.abs(m - oracle.mel_filterbank(16000, 500, 40, 0.0, 8000.0))) < 3e-7
     bad = mm.MfccConfig(16000, 512, 600, 160, 40, 13).to_c()
     assert lib.mmf_host_tables(ctypes.byref(bad), None, None, None) == _lib.MMF_ERR_INVALID
     assert b"at least input size" in lib.mmf_last_error()
