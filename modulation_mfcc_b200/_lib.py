@@ -17,7 +17,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libmmf_b200.so"
-SOURCES = ["stft_mel.cu", "post_kernels.cu", "change_fused.cu", "modspec_fast.cu", "modspec_tc.cu", "mfcc_tc.cu", "tc_fft.cu", "dft_generic.cu", "hilbert_fft.cu", "c_api.cu", "host_tables.cpp"]
+SOURCES = ["stft_mel.cu", "stft_mel_tc.cu", "post_kernels.cu", "change_fused.cu", "modspec_fast.cu", "modspec_tc.cu", "mfcc_tc.cu", "tc_fft.cu", "dft_generic.cu", "hilbert_fft.cu", "c_api.cu", "host_tables.cpp"]
 HEADERS = ["fft_regs.cuh", "stft_core.cuh", "sos_par.cuh", "mmf_internal.h", "../../include/mmf.h"]
 
 NVCC_FLAGS = [
@@ -58,6 +58,7 @@ MMF_FLAG_TC_FFT = 256
 MMF_FLAG_NO_TC_MODSPEC = 512
 MMF_FLAG_TC_DCT = 1024
 MMF_FLAG_MEL_WALK = 2048
+MMF_FLAG_NO_TC_MEL = 4096
 
 
 class mmf_config(C.Structure):

@@ -578,6 +578,18 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
     return cuda_fail(e, "uploading plan constants");
   }
 
+  // mel projection as a tcgen05 GEMM (default where it applies; stft_mel_tc.cu)
+  if (!(cfg->flags & (MMF_FLAG_NO_TC_MEL | MMF_FLAG_MEL_WALK | MMF_FLAG_MMA_MEL | MMF_FLAG_SPLIT_SMEM)) &&
+      stft_mel_tc_supported(cfg->n_fft, cfg->n_mels, cfg->hop_length, p->lead, p->packed)) {
+    std::vector<uint16_t> tab;
+    uint16_t* d_t = nullptr;
+    stft_mel_tc_table(mel, cfg->n_mels, p->F, tab);
+    if ((e = upload(&d_t, tab)) != cudaSuccess) {
+      mmf_plan_destroy(p);
+      return cuda_fail(e, "uploading the tensor-core mel operand");
+    }
+    p->d_mel_tc = d_t;
+  }
   if ((cfg->flags & MMF_FLAG_TC_DCT) && !(cfg->flags & MMF_FLAG_MMA_DCT) && mfcc_tc_supported(cfg->n_mfcc, cfg->n_mels)) {
     std::vector<uint16_t> tab;
     uint16_t* d_t = nullptr;
@@ -637,6 +649,7 @@ int mmf_plan_destroy(mmf_plan* p) {
   cudaFree(p->d_mg_step);
   cudaFree(p->d_mg_w);
   cudaFree(p->d_dct);
+  cudaFree(p->d_mel_tc);
   cudaFree(p->d_dct_bfrag);
   cudaFree(p->ws);
   cudaFree(p->host_ws);
@@ -772,6 +785,15 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   if (clipmax) {
     cudaError_t e = fill_i32_launch(clipmax, n_clips, (int)0x80800000, st)  /* key of -FLT_MAX */;
     if (e != cudaSuccess) return cuda_fail(e, "clipmax init");
+  }
+  // the mel projection on the tensor cores wherever the plan supports it -- a decision of the configuration alone, so
+  // that a clip's features never depend on the size or the chunking of the batch it came in
+  if (p->d_mel_tc && logmel && !power) {
+    cudaError_t e = stft_mel_tc_launch(tmap, tma ? 1 : 0, pcm, n_clips, n_samples, clip_stride, (int)T, c.hop_length, p->lead, c.n_mels, c.amin,
+                                       c.preemph, p->d_window, p->d_tw1, p->d_mel_tc, logmel, clipmax, p->sm_count, st);
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "stft_mel_tc_kernel launch");
+    return MMF_OK;
   }
   const long max_ctas = (long)p->ctas_per_sm * p->sm_count;
   const int grid = (int)std::min<long>(a.n_tiles, max_ctas);

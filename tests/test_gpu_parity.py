@@ -948,3 +948,92 @@ def test_zero_phase_filter_properties_full_size(cuda_device):
     assert float((fz - (2.0 * fx - 3.0 * fy)).abs().max()) < 1e-9 * scale
     ref = scipy.signal.sosfiltfilt(sos, x[:3].cpu().numpy())
     assert np.max(np.abs(fx[:3].cpu().numpy() - ref)) < 1e-9 * scale
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1 with the mel projection on the tcgen05 tensor cores (csrc/stft_mel_tc.cu)
+# ---------------------------------------------------------------------------------------------------
+TC_MEL_CASES = {
+    # name: (sr, winLen, tStep, n_mels, fmin, fmax, seconds, preemph)
+    "cfg2_40mel": (16000, 0.025, 0.01, 40, 0.0, 8000.0, 3.0, 0.0),
+    "mel64_fmin": (16000, 0.032, 0.008, 64, 60.0, 7600.0, 2.0, 0.0),
+    "mel26_8k": (8000, 0.03, 0.0125, 26, 0.0, 4000.0, 2.5, 0.0),
+    "mel13_oddhop": (16000, 0.02, 0.0100625, 13, 0.0, 8000.0, 2.0, 0.0),  # hop 161: scalar span loads
+    "mel40_preemph": (16000, 0.025, 0.01, 40, 0.0, 8000.0, 2.0, 0.97),
+}
+
+
+def _tc_cfg(name, flags):
+    sr, winLen, tStep, n_mels, fmin, fmax, secs, pre = TC_MEL_CASES[name]
+    win, hop = mm.frame_sizes(sr, winLen, tStep)
+    return mm.MfccConfig(sr, 512, win, hop, n_mels, 13, fmin, fmax, preemph=pre, flags=flags), secs
+
+
+def test_tcgen05_mel_plain_loader_is_bit_identical(cuda_device):
+    """Unaligned input (or MMF_FLAG_NO_TMA) takes the plain span loader of the same kernel: identical bits."""
+    torch = _torch()
+    cfg, secs = _tc_cfg("cfg2_40mel", 0)
+    y = synth_batch(303, 4, int(cfg.sample_rate * secs), cfg.sample_rate)
+    a, ka = mm.get_plan(cfg).logmel(y)
+    b, kb = mm.get_plan(mm.plan.replace(cfg, flags=_lib.MMF_FLAG_NO_TMA)).logmel(y)
+    assert torch.equal(a, b) and torch.equal(ka, kb)
+    # a row pitch that is not a multiple of 16 bytes cannot be described to the TMA unit
+    wide = torch.zeros((4, y.shape[1] + 1), device=cuda_device)
+    wide[:, : y.shape[1]] = torch.as_tensor(y)
+    c, kc = mm.get_plan(cfg).logmel(wide[:, : y.shape[1]])
+    assert torch.equal(a, c) and torch.equal(ka, kc)
+
+
+@pytest.mark.parametrize("name", list(TC_MEL_CASES))
+def test_logmel_tcgen05_mel_projection(name, cuda_device):
+    """The default K1 of batches (mel projection as a tcgen05 GEMM over 128-frame blocks, bf16 operand pairs) against
+    the oracle (north_star: 1e-4 on linear mel power) and against the CUDA-core kernel; per-clip maxima agree."""
+    cfg, secs = _tc_cfg(name, 0)
+    y = synth_batch(300, 5, int(cfg.sample_rate * secs), cfg.sample_rate)
+    y[3] *= 1000.0  # loud clip
+    y[4] *= 1e-4   # near-silent clip: most bands sit on the amin floor
+    lm, cmax = mm.get_plan(cfg).logmel(y)
+    cfg_ref, _ = _tc_cfg(name, _lib.MMF_FLAG_NO_TC_MEL)
+    lm_ref, cmax_ref = mm.get_plan(cfg_ref).logmel(y)
+    lm, lm_ref = lm.cpu().numpy(), lm_ref.cpu().numpy()
+    assert np.isfinite(lm).all()
+    assert _mel_rel_err(lm, lm_ref) <= LOGMEL_REL, name
+    km, kr = cmax.cpu().numpy().view(np.float32), cmax_ref.cpu().numpy().view(np.float32)
+    assert np.max(np.abs(km - kr)) < 4.4e-4, name  # per-clip max keys are the float bits of a non-negative-or-not dB value
+    if cfg.preemph == 0.0:
+        for i in range(y.shape[0]):
+            _, _, unclamped = _oracle_unclamped(y[i], cfg)
+            assert _mel_rel_err(lm[i], unclamped) <= LOGMEL_REL, (name, i)
+
+
+@pytest.mark.parametrize("n_samples", [1, 159, 160, 10079, 10080, 10240, 20319, 20320, 20480, 20481, 40000])
+def test_tcgen05_mel_ragged_lengths(n_samples, cuda_device):
+    """Frame counts around the 64-frame tile and 128-frame block edges (T = 1, 63, 64, 65, 127, 128, 129, ...): blocks
+    with one tile, partly filled tiles, rows beyond T never stored."""
+    cfg, _ = _tc_cfg("cfg2_40mel", 0)
+    y = synth_batch(301, 3, n_samples, cfg.sample_rate)
+    plan = mm.get_plan(cfg)
+    lm, cmax = plan.logmel(y)
+    lm = lm.cpu().numpy()
+    assert lm.shape[2] == 1 + n_samples // cfg.hop_length
+    for i in range(3):
+        _, _, unclamped = _oracle_unclamped(y[i], cfg)
+        assert _mel_rel_err(lm[i], unclamped) <= LOGMEL_REL, (n_samples, i)
+    ref, cref = mm.get_plan(_tc_cfg("cfg2_40mel", _lib.MMF_FLAG_NO_TC_MEL)[0]).logmel(y)
+    assert np.max(np.abs(cmax.cpu().numpy().view(np.float32) - cref.cpu().numpy().view(np.float32))) < 4.4e-4
+
+
+def test_tcgen05_mel_is_the_default_and_feeds_the_whole_path(cuda_device):
+    """n_fft = 512 with up to 64 bands takes the tcgen05 kernel without any flag; the composite call (MFCC, delta,
+    MFCC-change curve, modulation spectrum) stays within the north_star bounds of the oracle."""
+    sr = 16000
+    y = synth_batch(302, 160, sr * 2, sr)  # T = 201 -> 2 blocks per clip, 320 blocks
+    res = mm.mfcc_features_batch(y, sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
+    ref_flags = mm.mfcc_features_batch(y, sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13,
+                                       flags=_lib.MMF_FLAG_NO_TC_MEL)
+    assert not np.array_equal(res["mfcc"], ref_flags["mfcc"])  # different kernels really ran
+    for i in (0, 77, 159):
+        ref = oracle.mfcc_features(y[i], sr)
+        assert np.max(np.abs(res["mfcc"][i] - ref["mfcc"])) < ABS_TOL
+        assert np.max(np.abs(res["totChange"][i] - ref["totChange"])) < ABS_TOL
+        assert np.max(np.abs(res["modspec"][i] - ref["modspec"])) < ABS_TOL
