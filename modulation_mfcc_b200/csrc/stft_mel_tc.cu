@@ -163,6 +163,7 @@ struct StftTcArgs {
   int span_alloc;           // floats of a tile's PCM span, whole TMA boxes
   int lead;
   int vec_ok;
+  int win_lo, win_hi;       // 32-sample groups [win_lo, win_hi) of the zero-padded window that are not all zero
   int n_mels;
   float amin;
   float preemph;
@@ -271,12 +272,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float mx = -FLT_MAX;
     if (t < T) {
       float* dst = p.logmel + ((size_t)clip * p.n_mels + NBQ * cg) * T + t;
+      const int n_here = min(NBQ, p.n_mels - NBQ * cg);  // bands of this warp that exist
+      const float amin = p.amin;
 #pragma unroll
       for (int i = 0; i < NBQ; ++i) {
-        if (NBQ * cg + i < p.n_mels) {
+        if (i < n_here) {
           // 10*log10(x) = 10*log10(2) * log2(x); MUFU.LG2 is within 1e-6 dB here (x >= amin, never denormal)
-          const float db = 3.01029995663981195f * tc_log2(fmaxf(p.amin, d1[i] + d2[i]));
-          dst[(size_t)i * T] = db;
+          const float db = 3.01029995663981195f * tc_log2(fmaxf(amin, d1[i] + d2[i]));
+          *dst = db;
+          dst += T;
           mx = fmaxf(mx, db);
         }
       }
@@ -335,6 +339,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (p.preemph != 0.0f) {
           const long n_valid = p.n_samples - ((long)(t0 + f) * hop - kNfft / 2);
           ph_load_pre<kNfft>(v, s_span, off, hop, tau, wreg, p.preemph, n_valid);
+        } else if (hop == 160 && !(shift & 1)) {
+          ph_load_shared<kNfft, 5, true>(v, s_span, off, tau, wreg, p.win_lo, p.win_hi);
+        } else if (hop == 128 && !(shift & 1)) {
+          ph_load_shared<kNfft, 4, true>(v, s_span, off, tau, wreg, p.win_lo, p.win_hi);
+        } else if (hop == 256 && !(shift & 1)) {
+          ph_load_shared<kNfft, 8, true>(v, s_span, off, tau, wreg, p.win_lo, p.win_hi);
         } else if (p.vec_ok && !(shift & 1)) {
           ph_load<kNfft, true>(v, s_span, off, hop, tau, wreg);
         } else {
@@ -405,9 +415,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int c = 0; c < 8; ++c) {
           const float4 x = *reinterpret_cast<const float4*>(tsrc + 4 * c);
           const float xs[4] = {x.x, x.y, x.z, x.w};
-          float rs[4];
+          float ts[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) rs[e] = xs[e] - __uint_as_float(__float_as_uint(xs[e]) & 0xffff0000u);
+          for (int e = 0; e < 4; ++e) ts[e] = __uint_as_float(__float_as_uint(xs[e]) & 0xffff0000u);
+          // exact remainders, two per packed subtract
+          const pk r01 = ssub(pmake(xs[0], xs[1]), pmake(ts[0], ts[1])), r23 = ssub(pmake(xs[2], xs[3]), pmake(ts[2], ts[3]));
+          const float rs[4] = {plo(r01), phi(r01), plo(r23), phi(r23)};
           b1[2 * c] = __byte_perm(__float_as_uint(xs[0]), __float_as_uint(xs[1]), 0x7632);
           b1[2 * c + 1] = __byte_perm(__float_as_uint(xs[2]), __float_as_uint(xs[3]), 0x7632);
           b2[2 * c] = __byte_perm(__float_as_uint(rs[0]), __float_as_uint(rs[1]), 0x7632);
@@ -509,9 +522,12 @@ void stft_mel_tc_table(const std::vector<float>& mel, int n_mels, int F, std::ve
 
 cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float* pcm, long n_clips, long n_samples,
                                long clip_stride, int T, int hop,
-                               int lead, int n_mels, float amin, float preemph, const float* window, const float2* tw1,
-                               const void* wtab, float* logmel, int* clipmax, int sm_count, cudaStream_t st) {
+                               int lead, int n_mels, float amin, float preemph, const float* window, int win_lo,
+                               int win_hi, const float2* tw1, const void* wtab, float* logmel, int* clipmax,
+                               int sm_count, cudaStream_t st) {
   StftTcArgs a{};
+  a.win_lo = win_lo;
+  a.win_hi = win_hi;
   const long bpc = (T + kTcBlock - 1) / kTcBlock;
   if (bpc * n_clips > 0x7fffffffL) return cudaErrorInvalidValue;
   a.pcm = pcm;
