@@ -160,9 +160,10 @@ struct StftTcArgs {
   unsigned blocks_per_clip;
   int T;
   int hop;
-  int span_alloc;           // floats of a tile's PCM span, whole TMA boxes
+  int span_alloc;           // floats of a group's PCM span (16 frames of a tile), whole TMA boxes
   int lead;
   int vec_ok;
+  int stagger;              // start delay between the four groups of a CTA, cycles
   int win_lo, win_hi;       // 32-sample groups [win_lo, win_hi) of the zero-padded window that are not all zero
   int n_mels;
   float amin;
@@ -175,6 +176,15 @@ struct StftTcArgs {
 };
 
 // NBQ = bands per epilogue warp = nb / 4 (nb = n_mels rounded up to 16)
+//
+// Thread organisation.  Warp w = 4 cg + q.  The four warps with the same q (they share an SM sub-partition and,
+// by the hardware's rule, the TMEM lane quarter q) form a GROUP: per tile the group transforms frames
+// 16 q .. 16 q + 15 (eight half-warp frame pairs), transfers exactly those frames into lanes of quarter q, and
+// later reads them back from D.  Everything a group waits for inside a tile is produced by the group itself, so
+// its two barriers per tile are 128-thread named barriers and its PCM span has its own buffer and mbarrier: the
+// four groups drift apart (and are started staggered), one sub-partition's shared-memory phase running under the
+// others' arithmetic.  The only cross-group step is the MMA of a block: the last of the 16 warps to finish the
+// block's transfers issues it (nobody waits), and every warp picks the result up one transform later.
 template <int NBQ>
 __global__ void __launch_bounds__(kTcThreads, 1)
     stft_mel_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StftTcArgs p) {
@@ -184,16 +194,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr uint32_t kDCol = 2 * kTcACols;  // D1 at kDCol, D2 at kDCol + NB
   static_assert(2 * kTcACols + 2 * NB <= 512, "A (b1, b2) and D (D1, D2) must fit the 512 TMEM columns");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  float* s_span = reinterpret_cast<float*>(smem_raw);
-  pk* s_xb = reinterpret_cast<pk*>(s_span + p.span_alloc);                      // [32][kTcXS]
+  float* s_span = reinterpret_cast<float*>(smem_raw);                           // [4][span_alloc]
+  pk* s_xb = reinterpret_cast<pk*>(s_span + 4 * p.span_alloc);                  // [32][kTcXS]
   uint16_t* s_w = reinterpret_cast<uint16_t*>(s_xb + kTcSlots * kTcXS);         // [2 NB x 272] bf16
   c2* s_tw1 = reinterpret_cast<c2*>(s_w + 2 * NB * kTcKP);                      // [256]
   float2* s_win = reinterpret_cast<float2*>(s_tw1 + C::TW1);                    // [256] half-scaled window pairs
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_win + C::M);                  // [0] TMA, [1] MMA
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_win + C::M);                  // [0..3] TMA of group q, [4] MMA
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 5);
+  unsigned* s_cnt = s_tmem + 1;                                                 // warps that finished a block's transfers
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tau = tid & 15, slot = tid >> 4;
+  const int tau = tid & 15;
+  const int q = warp & 3, cg = warp >> 2, hw = lane >> 4;
 
   for (int i = tid; i < 2 * NB * kTcKP * 2 / 16; i += kTcThreads)
     reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wtab)[i];
@@ -213,8 +225,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    tc_mbar_init(&s_bar[0], 1);
-    tc_mbar_init(&s_bar[1], 1);
+    for (int i = 0; i < 5; ++i) tc_mbar_init(&s_bar[i], 1);
+    *s_cnt = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the operand table is read by the tensor core
@@ -224,18 +236,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t tmem = *s_tmem;
 
   // ---- roles
-  // transform: group `slot` owns frames 2 slot, 2 slot + 1 of the tile; its rows live in its exchange buffer
-  pk* xb = s_xb + slot * kTcXS;
-  float* row_a = reinterpret_cast<float*>(xb) + (slot & 1) * kTcOddShift;
+  // transform: half-warp (cg, hw) of group q owns frames 4 cg + 2 hw, + 1 of the group's 16; exchange buffer
+  // 8 q + 2 cg + hw (a group's buffers are consecutive: the row loads below rely on it, see kTcXS)
+  const int xbi = 8 * q + 2 * cg + hw;
+  pk* xb = s_xb + xbi * kTcXS;
+  float* row_a = reinterpret_cast<float*>(xb) + (xbi & 1) * kTcOddShift;
   const SlotRows rows{row_a, row_a + kTcRowB};
-  // transfer: warp (q, cg) moves frames 16 q .. 16 q + 15 of the tile, bins [64 cg, 64 cg + 64) (lanes 0-15 the
+  const int f_own = 4 * cg + 2 * hw;  // first of this half-warp's two frames within the group
+  // transfer: warp cg of group q moves the group's 16 frames (lane & 15), bins [64 cg, 64 cg + 64) (lanes 0-15 the
   // first 32 of them, lanes 16-31 the second 32) plus two of the eight tail columns (bins 256 ..)
-  const int q = warp & 3, cg = warp >> 2, hw = lane >> 4;
-  const int tf = 16 * q + (lane & 15);
-  const float* trow = reinterpret_cast<const float*>(s_xb + (tf >> 1) * kTcXS) + ((tf >> 1) & 1) * kTcOddShift +
-                      (tf & 1) * kTcRowB;
+  const int tfr = lane & 15;
+  const int tbi = 8 * q + (tfr >> 1);
+  const float* trow = reinterpret_cast<const float*>(s_xb + tbi * kTcXS) + (tbi & 1) * kTcOddShift + (tfr & 1) * kTcRowB;
   const float* tsrc = trow + 64 * cg + 32 * hw;
   const uint32_t lane_q = (uint32_t)(32 * q) << 16;
+  float* span = s_span + q * p.span_alloc;
+  uint64_t* bar_tma = &s_bar[q];
+  uint64_t* bar_mma = &s_bar[4];
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); };
 
   const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NB) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -244,19 +262,39 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int T = p.T, hop = p.hop, lead = p.lead;
   const uint32_t n_boxes = (uint32_t)p.span_alloc / kBox;
 
-  // tile sequence of this CTA: blocks blockIdx.x, + gridDim.x, ...; 1 or 2 tiles per block
+  // block sequence of this CTA: blocks blockIdx.x, + gridDim.x, ...; 1 or 2 tiles of 64 frames per block
   auto block_pos = [&](unsigned blk, int& clip, int& t0) {
     clip = (int)(blk / p.blocks_per_clip);
     t0 = (int)(blk - (unsigned)clip * p.blocks_per_clip) * kTcBlock;
   };
-  auto issue_span = [&](int clip, int t0) {  // warp 0: the tile's PCM span, one 1 KB box per TMA
-    const int g0 = (t0 * hop - kNfft / 2 - lead) & ~3;  // 16-byte aligned start (the remainder goes into `shift`)
+  // warp cg == 0 of the group: the PCM span of the group's 16 frames of tile t0, one 1 KB box per TMA
+  auto issue_span = [&](int clip, int t0) {
+    const int g0 = ((t0 + 16 * q) * hop - kNfft / 2 - lead) & ~3;  // 16-byte aligned start (remainder: `shift`)
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_mbar_expect_tx(&s_bar[0], (uint32_t)p.span_alloc * 4u);
+      tc_mbar_expect_tx(bar_tma, (uint32_t)p.span_alloc * 4u);
     }
     __syncwarp();
-    for (uint32_t bx = lane; bx < n_boxes; bx += 32) tc_tma_load_2d(s_span + bx * kBox, &tmap, g0 + (int)bx * kBox, clip, &s_bar[0]);
+    for (uint32_t bx = lane; bx < n_boxes; bx += 32) tc_tma_load_2d(span + bx * kBox, &tmap, g0 + (int)bx * kBox, clip, bar_tma);
+  };
+  // plain loader (no TMA): same span, same zero fill outside the clip
+  auto fill_span = [&](int clip, int t0) {
+    const long g0 = (long)(((t0 + 16 * q) * hop - kNfft / 2 - lead) & ~3);
+    const float* src = p.pcm + (size_t)clip * p.clip_stride;
+    for (int i = 32 * cg + lane; i < p.span_floats; i += 128) {
+      const long n = g0 + i;
+      span[i] = (n >= 0 && n < p.n_samples) ? __ldg(src + n) : 0.0f;
+    }
+    group_sync();
+  };
+  auto issue_mma = [&]() {  // one thread: D1 | D2 = b1 . [w1 | w2], D2 += b2 . w1 over the 17 K slabs
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < kTcSlabs; ++s) {
+      tc_mma_ts(tmem + kDCol, tmem + 8 * s, wdesc + 16 * s, idesc2, s > 0 ? 1u : 0u);
+      tc_mma_ts(tmem + kDCol + NB, tmem + kTcACols + 8 * s, wdesc + 16 * s, idesc1, 1u);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar_mma)) : "memory");
   };
   // D (tensor memory) -> log-mel rows of block (clip, t0): warp (q, cg) handles lanes 32 q .. 32 q + 31 (frames
   // t0 + 64 (lane / 16) + 16 q + lane % 16) and bands [NBQ cg, NBQ cg + NBQ)
@@ -288,29 +326,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0 && mx > -FLT_MAX) atomicMax(p.clipmax + clip, tc_float_key(mx));
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // D is overwritten after the next barrier
-  };
-
-  // plain loader (no TMA): same span, same zero fill outside the clip
-  auto fill_span = [&](int clip, int t0) {
-    const long g0 = (long)((t0 * hop - kNfft / 2 - lead) & ~3);
-    const float* src = p.pcm + (size_t)clip * p.clip_stride;
-    for (int i = tid; i < p.span_floats; i += kTcThreads) {
-      const long n = g0 + i;
-      s_span[i] = (n >= 0 && n < p.n_samples) ? __ldg(src + n) : 0.0f;
-    }
-    __syncthreads();
   };
 
   unsigned blk = blockIdx.x;
   int clip = 0, t0b = 0;
   if (blk < p.n_blocks) {
     block_pos(blk, clip, t0b);
-    if (p.use_tma && warp == 0) issue_span(clip, t0b);
+    if (p.use_tma && cg == 0) issue_span(clip, t0b);
+  }
+  // staggered start: group q begins q * stagger cycles late, so that the groups' phases interleave from the
+  // first tile on (they would otherwise leave the prologue barrier in lockstep)
+  if (p.stagger > 0 && q > 0) {
+    const long long t_start = clock64();
+    while (clock64() - t_start < (long long)q * p.stagger) {
+    }
   }
   uint32_t tma_par = 0, mma_par = 0;
-  bool mma_pending = false;   // block transferred, MMAs not issued yet (issued after the next barrier)
-  bool have_prev = false;     // a block whose D has not been written out yet
+  bool have_prev = false;  // a block whose MMAs are issued (or about to be) and whose D has not been written out yet
   int pclip = 0, pt0 = 0;
 
   while (blk < p.n_blocks) {
@@ -320,62 +352,46 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (nblk < p.n_blocks) block_pos(nblk, nclip, nt0b);
     for (int j = 0; j < n_tiles; ++j) {
       const int t0 = t0b + kTcTF * j;
-      const int g_first = t0 * hop - kNfft / 2 - lead;
+      const int g_first = (t0 + 16 * q) * hop - kNfft / 2 - lead;
       const int shift = g_first - (g_first & ~3);
-      // ---------------- load phase: two frames per group into registers
+      // ---------------- load phase: two frames per half-warp into registers
       V v[16];
       {
         float2 wreg[16];
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2) wreg[n2] = s_win[tau + C::TPF * n2];
-        const int f = 2 * slot;
-        const int off = shift + lead + f * hop;
+        const int off = shift + lead + f_own * hop;
         if (p.use_tma) {
-          tc_mbar_wait(&s_bar[0], tma_par);
+          tc_mbar_wait(bar_tma, tma_par);
           tma_par ^= 1u;
         } else {
           fill_span(clip, t0);  // (the previous tile's frames left the buffer before its first barrier)
         }
         if (p.preemph != 0.0f) {
-          const long n_valid = p.n_samples - ((long)(t0 + f) * hop - kNfft / 2);
-          ph_load_pre<kNfft>(v, s_span, off, hop, tau, wreg, p.preemph, n_valid);
+          const long n_valid = p.n_samples - ((long)(t0 + 16 * q + f_own) * hop - kNfft / 2);
+          ph_load_pre<kNfft>(v, span, off, hop, tau, wreg, p.preemph, n_valid);
         } else if (hop == 160 && !(shift & 1)) {
-          ph_load_shared<kNfft, 5, true>(v, s_span, off, tau, wreg, p.win_lo, p.win_hi);
+          ph_load_shared<kNfft, 5, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
         } else if (hop == 128 && !(shift & 1)) {
-          ph_load_shared<kNfft, 4, true>(v, s_span, off, tau, wreg, p.win_lo, p.win_hi);
+          ph_load_shared<kNfft, 4, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
         } else if (hop == 256 && !(shift & 1)) {
-          ph_load_shared<kNfft, 8, true>(v, s_span, off, tau, wreg, p.win_lo, p.win_hi);
+          ph_load_shared<kNfft, 8, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
         } else if (p.vec_ok && !(shift & 1)) {
-          ph_load<kNfft, true>(v, s_span, off, hop, tau, wreg);
+          ph_load<kNfft, true>(v, span, off, hop, tau, wreg);
         } else {
-          ph_load<kNfft, false>(v, s_span, off, hop, tau, wreg);
+          ph_load<kNfft, false>(v, span, off, hop, tau, wreg);
         }
       }
-      // every frame of the tile sits in registers: the span buffer is free; the previous tile's transfer (which
-      // read the exchange buffers and wrote the A operand) is complete
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (warp == 0 && p.use_tma) {
+      // the group's frames sit in registers: its span buffer is free, and its previous transfer (which read the
+      // group's exchange buffers) is complete
+      group_sync();
+      if (p.use_tma && cg == 0) {
         if (j + 1 < n_tiles)
           issue_span(clip, t0 + kTcTF);
         else if (nblk < p.n_blocks)
           issue_span(nclip, nt0b);
       }
-      if (tid == 256 && mma_pending) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int s = 0; s < kTcSlabs; ++s) {
-          tc_mma_ts(tmem + kDCol, tmem + 8 * s, wdesc + 16 * s, idesc2, s > 0 ? 1u : 0u);
-          tc_mma_ts(tmem + kDCol + NB, tmem + kTcACols + 8 * s, wdesc + 16 * s, idesc1, 1u);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&s_bar[1]))
-                     : "memory");
-      }
-      if (mma_pending) {
-        mma_pending = false;
-        have_prev = true;
-      }
-      // ---------------- transform (as stft_mel.cu, two frames per group on packed FP32)
+      // ---------------- transform (as stft_mel.cu, two frames per half-warp on packed FP32)
       ph_pass1<kNfft>(v, s_tw1, tau);
       __syncwarp();
       ph_x1_write<kNfft, 1>(v, xb, tau);
@@ -395,13 +411,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const V sh = tc_shfl(v[15 - r], src);
           bpart[r] = (tau == 0) ? v[(16 - r) & 15] : sh;
         }
-        __syncwarp();  // the group's exchange reads are done: its buffer now takes the two power rows
+        __syncwarp();  // the half-warp's exchange reads are done: its buffer now takes the two power rows
         ph_split_regs512_to(v, bpart, rows, 0, tau, wtau);
       }
-      __syncthreads();  // power rows complete
+      group_sync();  // the group's power rows are complete
       // ---------------- previous block: D -> log-mel (its MMAs ran underneath this tile's transform)
       if (j == 0 && have_prev) {
-        tc_mbar_wait(&s_bar[1], mma_par);
+        tc_mbar_wait(bar_mma, mma_par);
         mma_par ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         epilogue(pclip, pt0);
@@ -441,28 +457,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
     }
-    mma_pending = true;
+    // ---------------- the block's A operand is complete once all 16 warps have been here: the last one issues the MMAs
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const unsigned arrived = atomicAdd(s_cnt, 1u);
+      if ((arrived & 15u) == 15u) {
+        __threadfence_block();
+        issue_mma();
+      }
+    }
+    __syncwarp();
+    have_prev = true;
     pclip = clip;
     pt0 = t0b;
     blk = nblk;
     clip = nclip;
     t0b = nt0b;
   }
-  // ---------------- drain: MMAs and epilogue of the last block
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (mma_pending) {
-    if (tid == 256) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int s = 0; s < kTcSlabs; ++s) {
-        tc_mma_ts(tmem + kDCol, tmem + 8 * s, wdesc + 16 * s, idesc2, s > 0 ? 1u : 0u);
-        tc_mma_ts(tmem + kDCol + NB, tmem + kTcACols + 8 * s, wdesc + 16 * s, idesc1, 1u);
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&s_bar[1]))
-                   : "memory");
-    }
-    tc_mbar_wait(&s_bar[1], mma_par);
+  // ---------------- drain: epilogue of the last block
+  if (have_prev) {
+    tc_mbar_wait(bar_mma, mma_par);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     epilogue(pclip, pt0);
   }
@@ -479,11 +495,12 @@ static int tc_nb(int n_mels) { return (n_mels + 15) / 16 * 16; }
 
 static size_t tc_smem_bytes(int span_alloc, int nb) {
   using C = FftCfg<kNfft>;
-  return (size_t)span_alloc * 4 + (size_t)kTcSlots * kTcXS * 8 + (size_t)2 * nb * kTcKP * 2 + (size_t)C::TW1 * sizeof(c2) +
-         (size_t)C::M * 8 + 2 * 8 + 16;
+  return (size_t)4 * span_alloc * 4 + (size_t)kTcSlots * kTcXS * 8 + (size_t)2 * nb * kTcKP * 2 +
+         (size_t)C::TW1 * sizeof(c2) + (size_t)C::M * 8 + 5 * 8 + 16;
 }
 
-int stft_mel_tc_span_alloc(int hop, int lead) { return ((kTcTF - 1) * hop + kNfft + lead + 3 + kBox - 1) / kBox * kBox; }
+// floats of the PCM span of one group (16 frames), whole TMA boxes
+int stft_mel_tc_span_alloc(int hop, int lead) { return (15 * hop + kNfft + lead + 3 + kBox - 1) / kBox * kBox; }
 
 // n_fft = 512 on the packed two-frame transform, up to 64 bands, tile span + tables within one SM's shared memory
 bool stft_mel_tc_supported(int n_fft, int n_mels, int hop, int lead, int packed) {
@@ -524,7 +541,7 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
                                long clip_stride, int T, int hop,
                                int lead, int n_mels, float amin, float preemph, const float* window, int win_lo,
                                int win_hi, const float2* tw1, const void* wtab, float* logmel, int* clipmax,
-                               int sm_count, cudaStream_t st) {
+                               int sm_count, int stagger, cudaStream_t st) {
   StftTcArgs a{};
   a.win_lo = win_lo;
   a.win_hi = win_hi;
@@ -534,7 +551,8 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
   a.n_samples = n_samples;
   a.clip_stride = clip_stride;
   a.use_tma = use_tma;
-  a.span_floats = (kTcTF - 1) * hop + kNfft + lead + 3;
+  a.span_floats = 15 * hop + kNfft + lead + 3;
+  a.stagger = stagger;
   a.blocks_per_clip = (unsigned)bpc;
   a.n_blocks = (unsigned)(bpc * n_clips);
   a.T = T;
