@@ -1059,13 +1059,20 @@ static int run_post(mmf_plan* p, unsigned char*& cur, float* logmel, const int* 
   // shared memory directly; MFCC / delta go to HBM only if the caller asked for them.  Measured on the
   // bench workload: 1 % faster than the separate MFCC kernel without a delta output, 1 % slower with
   // one when the modulation spectrum follows -- hence the default.
+  // Batches: the output filter of the curve runs as its own launch (one warp per clip, all clips at once) instead of
+  // on ONE warp of the per-clip CTA while its other 11 wait (27 % of that kernel's stall samples, ncu round 2); the
+  // raw curve makes an 8 KB round trip per clip.  Same routine on the same buffer contents: bit-identical.
+  const bool split_out = out_iir && par_ok && n_clips >= 32;
   const bool fold = (c.flags & MMF_FLAG_FOLD_MFCC) || delta_out == nullptr;
   if (par_ok && fold && !(c.flags & (MMF_FLAG_SEPARATE_MFCC | MMF_FLAG_MMA_DCT)) && n_clips <= 0x7fffffff &&
       change_fused_lm_supported(pa, out_iir ? &po : nullptr, c.n_mfcc, c.n_mels, first, rows, T, &fsmem)) {
     const FusedMfccArgs lm{p->d_dct, p->nc_pad, logmel, clipmax, c.n_mels, c.top_db, mfcc_out, delta_out,
                            clamp_in_place};
+    double* raw = split_out ? (double*)carve(cur, (size_t)n_clips * T * 8) : nullptr;
     cudaError_t e = change_fused_launch(nullptr, n_clips, c.n_mfcc, first, rows, T, prm->diff_method, pa,
-                                        out_iir ? po : pa, prm->out_kind, tot, fsmem, &lm, st);
+                                        out_iir ? po : pa, split_out ? 1 : prm->out_kind, split_out ? raw : tot, fsmem,
+                                        &lm, st);
+    if (e == cudaSuccess && split_out) e = sosfiltfilt_par_launch(raw, 0, n_clips, T, T, 1, T, po, tot, T, st);
     if (e == cudaSuccess) return MMF_OK;
     if (e != cudaErrorNotSupported) return cuda_fail(e, "change_fused_kernel (from log-mel) launch");
   }
@@ -1074,8 +1081,11 @@ static int run_post(mmf_plan* p, unsigned char*& cur, float* logmel, const int* 
   // fused per-clip kernel: row filters, derivative + norm and the output filter with the
   // float64 rows resident in shared memory (script/mfcc.py:393-425)
   if (par_ok && change_fused_supported(pa, out_iir ? &po : nullptr, rows, T, &fsmem)) {
+    double* raw = split_out ? (double*)carve(cur, (size_t)n_clips * T * 8) : nullptr;
     cudaError_t e = change_fused_launch(mfcc, n_clips, c.n_mfcc, first, rows, T, prm->diff_method, pa,
-                                        out_iir ? po : pa, prm->out_kind, tot, fsmem, nullptr, st);
+                                        out_iir ? po : pa, split_out ? 1 : prm->out_kind, split_out ? raw : tot, fsmem,
+                                        nullptr, st);
+    if (e == cudaSuccess && split_out) e = sosfiltfilt_par_launch(raw, 0, n_clips, T, T, 1, T, po, tot, T, st);
     if (e == cudaSuccess) return MMF_OK;
     if (e != cudaErrorNotSupported) return cuda_fail(e, "change_fused_kernel launch");
   }

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstring>
 
+#include "fft_regs.cuh"
 #include "mmf_internal.h"
 
 namespace mmf {
@@ -115,6 +116,105 @@ __global__ void __launch_bounds__(kMfccThreads)
   }
 }
 
+// K3, fast form for n_mfcc <= 16 and n_mels a multiple of 8 (every BASELINE shape): same thread-per-frame layout and
+// the same FMA order as mfcc_kernel (so the MFCCs are bit-identical), but coefficient PAIRS are accumulated with
+// packed FFMA2 (half the issue slots of the contraction), the mel rows are walked with pointer steps instead of
+// 64-bit index products, and the loop body carries no predicates.  ncu of mfcc_kernel<16> on the bench shape:
+// 83.4 M warp instructions of which 21 M are the FFMAs -- issue-bound at 95 us for a 271 MB stream.
+template <int NP>
+__global__ void __launch_bounds__(kMfccThreads)
+    mfcc_pk_kernel(const float* __restrict__ dct_pad, float* logmel, const int* __restrict__ clipmax, long T, int n_mels,
+                   int n_mfcc, float top_db, float* __restrict__ mfcc, float* __restrict__ delta, int clamp_in_place) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_dct = sm;                 // [n_mels][16]
+  float* s_col = sm + n_mels * 16;   // [2 NP][kMfccThreads + 1]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_mels * 4; i += kMfccThreads)
+    reinterpret_cast<float4*>(s_dct)[i] = reinterpret_cast<const float4*>(dct_pad)[i];
+  __syncthreads();
+
+  const long clip = blockIdx.y;
+  const int halo = delta != nullptr ? 1 : 0;
+  const int per_block = kMfccThreads - 2 * halo;
+  const long t = (long)blockIdx.x * per_block - halo + tid;
+  const bool valid = t >= 0 && t < T;
+  const bool own = valid && tid >= halo && tid < kMfccThreads - halo;
+  const float thr = top_db >= 0.0f ? key_to_float(clipmax[clip]) - top_db : -FLT_MAX;
+
+  pk acc[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) acc[j] = pmake(0.0f, 0.0f);
+  // frames outside the clip (halo of the first / last block) read frame 0 / T - 1: finite, never stored
+  const long tc = t < 0 ? 0 : (t >= T ? T - 1 : t);
+  float* col = logmel + (size_t)clip * n_mels * T + tc;
+  const bool store_clamped = clamp_in_place && own;
+  {
+    const size_t T8 = (size_t)8 * T;
+    float cur[8], nxt[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cur[u] = __ldcs(col + (size_t)u * T);
+    const float* s_row = s_dct;
+    for (int m0 = 0; m0 < n_mels; m0 += 8) {
+      float* nrow = col + T8;
+      if (m0 + 8 < n_mels) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nxt[u] = __ldcs(nrow + (size_t)u * T);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float x = fmaxf(cur[u], thr);
+        if (store_clamped) col[(size_t)u * T] = x;
+        const pk xx = pmake(x, x);
+        const float4* d4 = reinterpret_cast<const float4*>(s_row + 16 * u);
+#pragma unroll
+        for (int j4 = 0; j4 < (NP + 1) / 2; ++j4) {
+          const float4 d = d4[j4];
+          acc[2 * j4] = sfma(pmake(d.x, d.y), xx, acc[2 * j4]);
+          if (2 * j4 + 1 < NP) acc[2 * j4 + 1] = sfma(pmake(d.z, d.w), xx, acc[2 * j4 + 1]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+      col = nrow;
+      s_row += 8 * 16;
+    }
+  }
+  float out[2 * NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    out[2 * j] = plo(acc[j]);
+    out[2 * j + 1] = phi(acc[j]);
+  }
+  if (own) {
+    float* dst = mfcc + (size_t)clip * n_mfcc * T + t;
+#pragma unroll
+    for (int j = 0; j < 2 * NP; ++j) {
+      if (j < n_mfcc) *dst = out[j];
+      dst += T;
+    }
+  }
+  if (delta != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 2 * NP; ++j) s_col[j * (kMfccThreads + 1) + tid] = out[j];
+    __syncthreads();
+    if (own) {
+      float* dst = delta + (size_t)clip * n_mfcc * T + t;
+      // np.gradient: one-sided at the clip's ends, central inside
+      const int lo = t == 0 ? 0 : -1, hi = t == T - 1 ? 0 : 1;
+      const float scale = (lo != 0 && hi != 0) ? 0.5f : 1.0f;
+#pragma unroll
+      for (int j = 0; j < 2 * NP; ++j) {
+        if (j < n_mfcc) {
+          const float* c = s_col + j * (kMfccThreads + 1) + tid;
+          // (c[1] - c[-1]) / 2 and (c[1] - c[0]) / 1 exactly as mfcc_kernel: division by 2 = multiplication by 0.5
+          *dst = T == 1 ? 0.0f : (c[hi] - c[lo]) * scale;
+        }
+        dst += T;
+      }
+    }
+  }
+}
+
 cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const int* clipmax, long n_clips, long T,
                         int n_mels, int n_mfcc, float top_db, float* mfcc, float* delta, int clamp_in_place,
                         cudaStream_t st) {
@@ -123,6 +223,26 @@ cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const i
   dim3 grid((unsigned)((T + per_block - 1) / per_block), (unsigned)n_clips);
   int nc = n_mfcc <= 16 ? 16 : (n_mfcc <= 32 ? 32 : (n_mfcc <= 64 ? 64 : 128));
   size_t smem = ((size_t)n_mels * nc + (size_t)nc * (kMfccThreads + 1)) * sizeof(float);
+  if (nc == 16 && nc_pad == 16 && n_mels % 8 == 0 && n_mels >= 8) {
+    const int np = n_mfcc <= 8 ? 4 : (n_mfcc + 1) / 2;
+#define MMF_MFCC_PK_CASE(N)                                                                                        \
+  case N: {                                                                                                        \
+    MMF_SMEM_ONCE(mfcc_pk_kernel<N>, 200 * 1024);                                                                  \
+    mfcc_pk_kernel<N><<<grid, kMfccThreads, smem, st>>>(dct_pad, logmel, clipmax, T, n_mels, n_mfcc, top_db, mfcc, \
+                                                        delta, clamp_in_place);                                    \
+    break;                                                                                                         \
+  }
+    switch (np) {
+      MMF_MFCC_PK_CASE(4)
+      MMF_MFCC_PK_CASE(5)
+      MMF_MFCC_PK_CASE(6)
+      MMF_MFCC_PK_CASE(7)
+      MMF_MFCC_PK_CASE(8)
+    }
+#undef MMF_MFCC_PK_CASE
+    count_launch();
+    return cudaGetLastError();
+  }
 #define MMF_MFCC_CASE(N)                                                                                         \
   case N: {                                                                                                      \
     MMF_SMEM_ONCE(mfcc_kernel<N>, 200 * 1024);                                                                   \

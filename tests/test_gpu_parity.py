@@ -1037,3 +1037,23 @@ def test_tcgen05_mel_is_the_default_and_feeds_the_whole_path(cuda_device):
         assert np.max(np.abs(res["mfcc"][i] - ref["mfcc"])) < ABS_TOL
         assert np.max(np.abs(res["totChange"][i] - ref["totChange"])) < ABS_TOL
         assert np.max(np.abs(res["modspec"][i] - ref["modspec"])) < ABS_TOL
+
+
+def test_batch_size_never_changes_a_clip(cuda_device):
+    """Kernel selection by batch size (per-clip fused output filter below 32 clips, one launch over all clips above)
+    must not change a single bit of a clip's features; neither may the position of the clip in the batch."""
+    sr = 16000
+    y = synth_batch(304, 40, sr * 3, sr)
+    big = mm.mfcc_features_batch(y, sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
+    for i in (0, 17, 39):
+        one = mm.mfcc_features_batch(y[i : i + 1], sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
+        for k in ("mfcc", "delta", "totChange", "modspec", "band_energy"):
+            assert np.array_equal(one[k][0], big[k][i]), (k, i)
+    small = mm.mfcc_features_batch(y[8:20], sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
+    for k in ("mfcc", "delta", "totChange", "modspec", "band_energy"):
+        assert np.array_equal(small[k], big[k][8:20]), k
+    # the GUI's own call (no delta output -> MFCC stage folded into the per-clip kernel), both batch regimes
+    kw = dict(KW_GUI, tStep=0.01, n_mels=40, maxFreq=8000)
+    c1, T1 = mm.get_MFCCS_change(y[5], sr, **kw)
+    cb, Tb = mm.get_MFCCS_change_batch(y, sr, **{k: v for k, v in kw.items() if k != "channelN"})
+    assert np.array_equal(c1, cb[5]) and np.array_equal(T1, Tb)
