@@ -288,8 +288,9 @@ def _read_audio(path: str, sr: float, device=None, *, to_host: bool = True):
     Decode/resample sits *before* the measured path.
     The file is parsed on the host (scipy's WAV reader); 16-bit PCM is scaled on the
     device (``mmf_pcm16_to_f32``) and the rate conversion is a polyphase resampler on
-    the device (``mmf_resample_poly``, scipy.signal.resample_poly semantics).  librosa
-    resamples with soxr_hq: same band limits, not bit-identical."""
+    the device (``mmf_resample_poly``: polyphase FIR with libsoxr HQ's band limits -- pass band to 0.913
+    of the lower Nyquist, 120 dB -- which is what librosa.load applies; within 1e-5 of the ideal band-limited
+    resampling below the band edge, not bit-identical to libsoxr: DESIGN.md section 6b)."""
     from scipy.io import wavfile
 
     torch = _torch()
@@ -320,7 +321,7 @@ def _read_audio(path: str, sr: float, device=None, *, to_host: bool = True):
             from fractions import Fraction
 
             fr = Fraction(float(sr) / float(file_sr)).limit_denominator(1000)
-            y = plan.resample_poly(y, fr.numerator, fr.denominator)
+            y = plan.resample_poly(y, fr.numerator, fr.denominator, quality="hq")
     except MmfError as e:
         _raise_from(e)
     return np.ascontiguousarray(y.cpu().numpy()) if to_host else y

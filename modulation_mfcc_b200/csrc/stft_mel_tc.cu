@@ -454,10 +454,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         tc_tmem_st16x1(a_lane + 128 + 2 * cg, t1);
         tc_tmem_st16x1(a_lane + kTcACols + 128 + 2 * cg, t2);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // (no wait here: the stores only have to be complete when this warp reports the block below)
       }
     }
     // ---------------- the block's A operand is complete once all 16 warps have been here: the last one issues the MMAs
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) {

@@ -123,6 +123,41 @@ def _stream_ptr(device) -> int:
     return int(_torch().cuda.current_stream(device).cuda_stream)
 
 
+def design_resample_filter(n_in: int, up: int, down: int, quality: str = "scipy"):
+    """Taps (float32, zero-padded for the polyphase bookkeeping), samples to drop at the front of the full
+    convolution, and output length, for ``y = upfirdn(h, x, up, down)[n_pre_remove : n_pre_remove + n_out]``.
+
+    ``"scipy"`` restates scipy/signal/_signaltools.py resample_poly (filter design and edge bookkeeping) -- the
+    output is bit-compatible with it up to float32 rounding.  ``"hq"`` keeps the bookkeeping and swaps the filter:
+    Kaiser-windowed sinc with the transition band 0.913 .. 1.0 of the lower Nyquist at 120 dB (beta 12.27,
+    90 taps per phase side), i.e. libsoxr HQ's band limits -- what ``librosa.load`` applies at script/mfcc.py:373.
+    Content below 0.9 of the lower Nyquist comes through within 1e-5 of the ideal band-limited resampling
+    (tests/test_host.py::test_hq_resampler_is_transparent_below_the_band_edge); libsoxr's own output cannot be
+    compared here (not installed, no network)."""
+    import scipy.signal
+    from scipy.signal._upfirdn import _output_len
+
+    n_out = n_in * up
+    n_out = n_out // down + bool(n_out % down)
+    max_rate = max(up, down)
+    if quality == "scipy":
+        half_len = 10 * max_rate
+        h = scipy.signal.firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0))
+    elif quality == "hq":
+        half_len = 90 * max_rate
+        h = scipy.signal.firwin(2 * half_len + 1, 0.9565 / max_rate, window=("kaiser", 12.27))
+    else:
+        raise ValueError("quality must be 'scipy' or 'hq'")
+    h = h.astype(np.float32) * up
+    n_pre_pad = down - half_len % down
+    n_post_pad = 0
+    n_pre_remove = (half_len + n_pre_pad) // down
+    while _output_len(len(h) + n_pre_pad + n_post_pad, n_in, up, down) < n_out + n_pre_remove:
+        n_post_pad += 1
+    h = np.concatenate((np.zeros(n_pre_pad, dtype=h.dtype), h, np.zeros(n_post_pad, dtype=h.dtype)))
+    return np.ascontiguousarray(h, dtype=np.float32), n_pre_remove, n_out
+
+
 class Plan:
     """Device-resident plan (``mmf_plan``).  Not thread-safe: one plan per host thread."""
 
@@ -421,14 +456,15 @@ class Plan:
         check(_lib.lib().mmf_pcm16_to_f32(self._h, x.data_ptr(), x.numel(), y.data_ptr(), _stream_ptr(x.device)))
         return y
 
-    def resample_poly(self, x, up: int, down: int):
-        """``scipy.signal.resample_poly(x, up, down, axis=-1)`` (default Kaiser-5 FIR, constant
-        padding) for float32 rows on the device.  The filter is designed on the host exactly as
-        scipy designs it; the polyphase convolution runs on the GPU."""
+    def resample_poly(self, x, up: int, down: int, quality: str = "scipy"):
+        """Rational-rate conversion of float32 rows on the device (polyphase FIR, float64 accumulation).
+
+        ``quality="scipy"``: exactly ``scipy.signal.resample_poly(x, up, down, axis=-1)`` (Kaiser-5 FIR, 10 taps per
+        phase side, constant padding).  ``quality="hq"``: the band limits of libsoxr's HQ recipe that
+        ``librosa.load(sr=...)`` uses at script/mfcc.py:373 (pass band to 0.913 of the lower Nyquist, stop band from
+        the Nyquist, 120 dB).  The filter is designed on the host (:func:`design_resample_filter`)."""
         torch = _torch()
         import math
-
-        import scipy.signal
 
         x = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
         x = x.to(device=torch.device("cuda", self.cfg.device), dtype=torch.float32)
@@ -441,22 +477,7 @@ class Plan:
         n_in = x.shape[-1]
         if up == 1 and down == 1:
             return x[0] if squeeze else x
-        n_out = n_in * up
-        n_out = n_out // down + bool(n_out % down)
-        # scipy/signal/_signaltools.py resample_poly: filter design and edge bookkeeping
-        max_rate = max(up, down)
-        half_len = 10 * max_rate
-        h = scipy.signal.firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)).astype(np.float32) * up
-        n_pre_pad = down - half_len % down
-        n_post_pad = 0
-        n_pre_remove = (half_len + n_pre_pad) // down
-
-        from scipy.signal._upfirdn import _output_len
-
-        while _output_len(len(h) + n_pre_pad + n_post_pad, n_in, up, down) < n_out + n_pre_remove:
-            n_post_pad += 1
-        h = np.concatenate((np.zeros(n_pre_pad, dtype=h.dtype), h, np.zeros(n_post_pad, dtype=h.dtype)))
-        h = np.ascontiguousarray(h, dtype=np.float32)
+        h, n_pre_remove, n_out = design_resample_filter(n_in, up, down, quality)
         y = torch.empty((x.shape[0], n_out), device=x.device, dtype=torch.float32)
         for c0 in range(0, x.shape[0], 65535):
             xs = x[c0 : c0 + 65535]
@@ -652,6 +673,7 @@ def clear_plans() -> None:
 
 
 __all__ = [
+    "design_resample_filter",
     "MfccConfig",
     "Plan",
     "get_plan",

@@ -734,9 +734,20 @@ def test_load_channel_wav_pcm16_and_resample(cuda_device, tmp_path):
     path = str(tmp_path / "clip.wav")
     wavfile.write(path, sr_file, pcm)
     got = mm.load_channel(path, sr)
-    want = scipy.signal.resample_poly(pcm.astype(np.float64) / 32768.0, 160, 441)
+    # the loader converts the rate with libsoxr HQ's band limits (what librosa.load applies at script/mfcc.py:373);
+    # the device kernel against the same taps applied by scipy's upfirdn in float64
+    from modulation_mfcc_b200.plan import design_resample_filter
+
+    h, n_pre, n_out = design_resample_filter(len(pcm), 160, 441, "hq")
+    want = scipy.signal.upfirdn(h.astype(np.float64), pcm.astype(np.float64) / 32768.0, 160, 441)[n_pre : n_pre + n_out]
     assert got.dtype == np.float32 and got.shape == want.shape
-    assert np.max(np.abs(got - want)) < 2e-5
+    assert np.max(np.abs(got - want)) < 2e-6
+    # ... and a pure tone below the band edge against the ideal resampling (through the 16-bit file: 2^-16 rounding)
+    tone = np.sin(2 * np.pi * 5000.0 * np.arange(sr_file) / sr_file) * 0.5
+    wavfile.write(str(tmp_path / "tone.wav"), sr_file, np.round(tone * 32767.0).astype(np.int16))
+    got_t = mm.load_channel(str(tmp_path / "tone.wav"), sr)
+    ideal = np.sin(2 * np.pi * 5000.0 * np.arange(len(got_t)) / sr) * 0.5 * 32767.0 / 32768.0
+    assert np.max(np.abs(got_t - ideal)[800:-800]) < 4e-5
     same = mm.load_channel(path, sr_file)
     assert np.array_equal(same, pcm.astype(np.float32) / 32768.0)
     # a path goes straight through get_MFCCS_change like an array does (script/mfcc.py:372-380)
