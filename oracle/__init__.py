@@ -7,13 +7,15 @@ there only as the checker or as the timed CPU baseline.  The product package
 (``modulation_mfcc_b200``) never imports this package and raises loudly when its
 CUDA library is missing.
 
-PARITY UNPINNED: the reference repository (aaron-randreth/modulation-mfcc) has no
-tests, golden vectors or fixtures for this path, and its own implementation
-cannot be imported in this image (``script/mfcc.py:8,18-23,27`` import librosa,
-parselmouth and pyqtgraph, none of which is installed; no network).  The
-arithmetic of the path lives in un-vendored, un-pinned third-party packages
-(``requirements.txt:1-12``: librosa, scipy, numpy<2, findiff).  This oracle
-therefore
+PARITY: pinned to the reference's executed code for everything but the librosa call.
+The reference repository (aaron-randreth/modulation-mfcc) has no tests, golden vectors
+or fixtures for this path, and ``script/mfcc.py:8,18-23,27`` import librosa, parselmouth
+and pyqtgraph, none of which is installed (no network).  ``oracle/ref_loader.py`` runs
+``script/mfcc.py`` and ``script/calc.py`` UNMODIFIED with stub modules for those
+packages; ``tests/test_reference_pin.py`` checks this restatement bit for bit against
+their outputs (``tests/golden/ref_outputs.npz``).  The one step that remains a
+restatement is ``librosa.feature.mfcc`` itself (an un-vendored, un-pinned dependency,
+``requirements.txt:1-12``), cross-checked against torchaudio and transformers.  This oracle
 
 * restates the librosa call chain behind ``librosa.feature.mfcc`` /
   ``librosa.feature.rms`` (librosa >= 0.10 semantics: ``center=True``,
