@@ -599,7 +599,6 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
           p->win_hi = std::max(p->win_hi, n2 + 1);
         }
     if (p->win_hi <= p->win_lo) p->win_lo = 0, p->win_hi = 16;
-    if (const char* e = std::getenv("MMF_TC_STAGGER")) p->tc_stagger = std::max(0, std::atoi(e));  // timing only
   }
   if ((cfg->flags & MMF_FLAG_TC_DCT) && !(cfg->flags & MMF_FLAG_MMA_DCT) && mfcc_tc_supported(cfg->n_mfcc, cfg->n_mels)) {
     std::vector<uint16_t> tab;
@@ -801,7 +800,7 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   // that a clip's features never depend on the size or the chunking of the batch it came in
   if (p->d_mel_tc && logmel && !power) {
     cudaError_t e = stft_mel_tc_launch(tmap, tma ? 1 : 0, pcm, n_clips, n_samples, clip_stride, (int)T, c.hop_length, p->lead, c.n_mels, c.amin,
-                                       c.preemph, p->d_window, p->win_lo, p->win_hi, p->d_tw1, p->d_mel_tc, logmel, clipmax, p->sm_count, p->tc_stagger, st);
+                                       c.preemph, p->d_window, p->win_lo, p->win_hi, p->d_tw1, p->d_mel_tc, logmel, clipmax, p->sm_count, st);
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "stft_mel_tc_kernel launch");
     return MMF_OK;

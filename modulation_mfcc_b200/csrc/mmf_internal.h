@@ -85,7 +85,7 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
                                long clip_stride, int T, int hop,
                                int lead, int n_mels, float amin, float preemph, const float* window, int win_lo,
                                int win_hi, const float2* tw1, const void* wtab, float* logmel, int* clipmax,
-                               int sm_count, int stagger, cudaStream_t st);
+                               int sm_count, cudaStream_t st);
 
 // ---- generic n_fft (anything but a power of two in [256, 4096]): FP32 matrix-product DFT (dft_generic.cu)
 void dft_generic_table(int n_fft, const std::vector<float>& window, std::vector<float>& tab, int* ld_out);
@@ -263,7 +263,6 @@ struct mmf_plan {
   int2* d_mg_seg = nullptr;
   int2* d_mg_step = nullptr;
   float4* d_mg_w = nullptr;
-  int tc_stagger = 2000;        // start delay between the four groups of a tcgen05 K1 CTA, cycles (MMF_TC_STAGGER)
   int win_lo = 0, win_hi = 16;  // 32-sample groups of the zero-padded window (n_fft = 512) that are not all zero
   void* d_mel_tc = nullptr;  // bf16 [w1 ; w2] operand of the tcgen05 mel projection (null: not in use)
   float* d_dct = nullptr;  // [n_mels][nc_pad]

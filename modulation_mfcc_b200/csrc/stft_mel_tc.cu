@@ -163,7 +163,6 @@ struct StftTcArgs {
   int span_alloc;           // floats of a group's PCM span (16 frames of a tile), whole TMA boxes
   int lead;
   int vec_ok;
-  int stagger;              // start delay between the four groups of a CTA, cycles
   int win_lo, win_hi;       // 32-sample groups [win_lo, win_hi) of the zero-padded window that are not all zero
   int n_mels;
   float amin;
@@ -182,9 +181,10 @@ struct StftTcArgs {
 // 16 q .. 16 q + 15 (eight half-warp frame pairs), transfers exactly those frames into lanes of quarter q, and
 // later reads them back from D.  Everything a group waits for inside a tile is produced by the group itself, so
 // its two barriers per tile are 128-thread named barriers and its PCM span has its own buffer and mbarrier: the
-// four groups drift apart (and are started staggered), one sub-partition's shared-memory phase running under the
-// others' arithmetic.  The only cross-group step is the MMA of a block: the last of the 16 warps to finish the
-// block's transfers issues it (nobody waits), and every warp picks the result up one transform later.
+// four groups drift apart, one sub-partition's shared-memory phase running under the others' arithmetic (a
+// deliberate start stagger of up to 4000 cycles between the groups measured no different: DESIGN.md section 6a).
+// The only cross-group step is the MMA of a block: the last of the 16 warps to finish the block's transfers
+// issues it (nobody waits), and every warp picks the result up one transform later.
 template <int NBQ>
 __global__ void __launch_bounds__(kTcThreads, 1)
     stft_mel_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StftTcArgs p) {
@@ -333,13 +333,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (blk < p.n_blocks) {
     block_pos(blk, clip, t0b);
     if (p.use_tma && cg == 0) issue_span(clip, t0b);
-  }
-  // staggered start: group q begins q * stagger cycles late, so that the groups' phases interleave from the
-  // first tile on (they would otherwise leave the prologue barrier in lockstep)
-  if (p.stagger > 0 && q > 0) {
-    const long long t_start = clock64();
-    while (clock64() - t_start < (long long)q * p.stagger) {
-    }
   }
   uint32_t tma_par = 0, mma_par = 0;
   bool have_prev = false;  // a block whose MMAs are issued (or about to be) and whose D has not been written out yet
@@ -542,7 +535,7 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
                                long clip_stride, int T, int hop,
                                int lead, int n_mels, float amin, float preemph, const float* window, int win_lo,
                                int win_hi, const float2* tw1, const void* wtab, float* logmel, int* clipmax,
-                               int sm_count, int stagger, cudaStream_t st) {
+                               int sm_count, cudaStream_t st) {
   StftTcArgs a{};
   a.win_lo = win_lo;
   a.win_hi = win_hi;
@@ -553,7 +546,6 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
   a.clip_stride = clip_stride;
   a.use_tma = use_tma;
   a.span_floats = 15 * hop + kNfft + lead + 3;
-  a.stagger = stagger;
   a.blocks_per_clip = (unsigned)bpc;
   a.n_blocks = (unsigned)(bpc * n_clips);
   a.T = T;
