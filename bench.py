@@ -320,13 +320,16 @@ def run_b200(args):
             gather.push(res_w[0]["totChange"], (rank * n_keep + i) * CLIPS)
         gather.finish()
     del res_w
-    torch.cuda.synchronize()
-    barrier()
+    # the clock sampler (a thread polling NVML / nvidia-smi) is started BEFORE the barrier: starting it between the
+    # barrier and the first event skews the ranks by milliseconds, and with a gather that ends on a device-side
+    # barrier over all ranks every millisecond of start skew is billed to the ranks that started early (measured at
+    # 8 GPUs: 1.08 ms per step in a 30-step region against 0.92 ms in the 2 s sustained loop of the same run)
     sampler = ClockSampler(local)
     sampler.start()
     lib.mmf_launch_count(1)
-    torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    barrier()
     ev0.record()
     for i in range(args.steps):
         last = step(True, i)
@@ -356,10 +359,10 @@ def run_b200(args):
     if not args.no_sustained:
         n_sus = max(200, int(2.2 / (ms_step * 1e-3)))
         ps = PowerSampler(local)
-        torch.cuda.synchronize()
-        barrier()
         ps.start()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        barrier()
         s0.record()
         for i in range(n_sus):
             step(False, i)
