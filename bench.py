@@ -153,6 +153,8 @@ class ClockSampler(threading.Thread):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._stop_evt = threading.Event()
+        self.armed = False  # the thread records only between arm() and stop(): samples taken while ranks wait at a
+        self._names = {}    # barrier would put idle clocks into the median
         self.ok = False
         try:
             import pynvml
@@ -176,21 +178,42 @@ class ClockSampler(threading.Thread):
             "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
             "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
         }
+        self._names = names
         while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
+            if self.armed:
+                self.sample()
             time.sleep(self.period)
 
+    def sample(self):
+        """One reading of the SM clock and the throttle reasons (any thread)."""
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in self._names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def poll_until(self, event, period: float = 0.002):
+        """Sample from the calling thread until the CUDA event has completed: the host enqueues a timed region far
+        ahead of the GPU, so this loop runs while the kernels do -- it does not depend on the sampler thread getting
+        the GIL (one run of this bench came back with a single sample in a 46 ms region)."""
+        if not self.ok:
+            return
+        while not event.query():
+            self.sample()
+            time.sleep(period)
+
+    def arm(self):
+        self.armed = True
+
     def stop(self):
+        self.armed = False
         self._stop_evt.set()
         self.join(timeout=2)
         med = statistics.median(self.samples) if self.samples else None
@@ -230,14 +253,18 @@ class PowerSampler(ClockSampler):
     def run(self):
         if not self.ok:
             return
-        nv = self.nv
         while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
-            except Exception:
-                pass
+            if self.armed:
+                self.sample()
             time.sleep(self.period)
+
+    def sample(self):
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
 
 
 def run_b200(args):
@@ -330,6 +357,7 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     barrier()
+    sampler.arm()
     ev0.record()
     for i in range(args.steps):
         last = step(True, i)
@@ -337,6 +365,7 @@ def run_b200(args):
     if gather is not None:
         gathered = gather.finish()  # every rank's curves of every step have landed before the clock stops
     ev1.record()
+    sampler.poll_until(ev1)
     torch.cuda.synchronize()
     barrier()
     launches = int(lib.mmf_launch_count(0))
@@ -363,12 +392,14 @@ def run_b200(args):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         barrier()
+        ps.arm()
         s0.record()
         for i in range(n_sus):
             step(False, i)
         if gather is not None:
             gather.finish()
         s1.record()
+        ps.poll_until(s1, 0.01)
         torch.cuda.synchronize()
         sus_ms = max_over_ranks(s0.elapsed_time(s1))
         pc = ps.stop()

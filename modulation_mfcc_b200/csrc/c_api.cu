@@ -798,7 +798,7 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   }
   // the mel projection on the tensor cores wherever the plan supports it -- a decision of the configuration alone, so
   // that a clip's features never depend on the size or the chunking of the batch it came in
-  if (p->d_mel_tc && logmel && !power) {
+  if (p->d_mel_tc && logmel && !power && ((T + 127) / 128) * n_clips < 0x7fffffffLL) {
     cudaError_t e = stft_mel_tc_launch(tmap, tma ? 1 : 0, pcm, n_clips, n_samples, clip_stride, (int)T, c.hop_length, p->lead, c.n_mels, c.amin,
                                        c.preemph, p->d_window, p->win_lo, p->win_hi, p->d_tw1, p->d_mel_tc, logmel, clipmax, p->sm_count, st);
     count_launch();

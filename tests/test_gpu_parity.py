@@ -1068,3 +1068,47 @@ def test_batch_size_never_changes_a_clip(cuda_device):
     c1, T1 = mm.get_MFCCS_change(y[5], sr, **kw)
     cb, Tb = mm.get_MFCCS_change_batch(y, sr, **{k: v for k, v in kw.items() if k != "channelN"})
     assert np.array_equal(c1, cb[5]) and np.array_equal(T1, Tb)
+
+
+def test_tcgen05_mel_is_deterministic_under_load(cuda_device):
+    """compute-sanitizer is not available on the GPU pool, so hazards in the kernel's hand-rolled synchronisation
+    (named barriers per group, TMA / MMA mbarriers, the last-arriver MMA issue, exchange buffers reused as row
+    staging) are hunted the blunt way: a batch with ~14 blocks per CTA, 25 launches, every bit equal -- and equal
+    to the same clips run in small batches, where each CTA sees a different block sequence."""
+    torch = _torch()
+    cfg, _ = _tc_cfg("cfg2_40mel", 0)
+    pcm = mm.synth_batch_device(260, 16000 * 10, 16000, seed=77, device=cuda_device)
+    plan = mm.get_plan(cfg)
+    lm0, k0 = plan.logmel(pcm)
+    lm0, k0 = lm0.clone(), k0.clone()
+    for _ in range(25):
+        lm, k = plan.logmel(pcm)
+        assert torch.equal(lm, lm0) and torch.equal(k, k0)
+    for b0 in (0, 37, 255):
+        lm, k = plan.logmel(pcm[b0 : b0 + 5])
+        assert torch.equal(lm, lm0[b0 : b0 + 5]) and torch.equal(k, k0[b0 : b0 + 5])
+
+
+def test_cfg3_full_size_properties(cuda_device):
+    """BASELINE configs[2] at its stated size (512 x 10 s at 44.1 kHz, n_fft 2048, 128 mel, 20 MFCC): an oracle
+    sample, finiteness, batch-position independence and gain linearity on the whole batch."""
+    torch = _torch()
+    sr, n, B = 44100, 441000, 512
+    pcm = mm.synth_batch_device(B, n, sr, seed=4242, device=cuda_device)
+    fx = mm.FeatureExtractor(sr, tStep=0.01, winLen=0.025, n_fft=2048, n_mels=128, n_mfcc=20)
+    res = fx(pcm, want_logmel=False)
+    T = 1 + n // 441
+    assert res["mfcc"].shape == (B, 20, T)
+    for v in res.values():
+        assert v is None or bool(torch.isfinite(v).all())
+    for i in (0, 511):
+        ref = oracle.mfcc_features(pcm[i].cpu().numpy(), sr, n_fft=2048, n_mels=128, n_mfcc=20)
+        assert np.max(np.abs(res["mfcc"][i].cpu().numpy() - ref["mfcc"])) < ABS_TOL
+        assert np.max(np.abs(res["totChange"][i].cpu().numpy() - ref["totChange"])) < ABS_TOL
+        assert np.max(np.abs(res["modspec"][i].cpu().numpy() - ref["modspec"])) < ABS_TOL
+    perm = torch.randperm(B, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(3))
+    res_p = fx(pcm[perm].contiguous(), want_logmel=False)
+    assert torch.equal(res_p["mfcc"], res["mfcc"][perm]) and torch.equal(res_p["totChange"], res["totChange"][perm])
+    lm1, _ = fx.plan.logmel(pcm[:32])
+    lm2, _ = fx.plan.logmel(pcm[:32] * 0.5)
+    assert float((lm1 - lm2 - 20 * np.log10(2.0)).abs().max()) < 2e-4
