@@ -72,7 +72,7 @@ typedef struct {
                                      (n_mfcc <= 16, n_mels <= 96) instead of the FP32 FMA kernel; measured equal */
 #define MMF_FLAG_MEL_WALK 2048     /* mel projection with the per-bin sparse walk on the [bin][frame] power tile instead of
                                       the grouped walk (four bins per step, packed FFMA2) on the bin-pair tile */
-#define MMF_FLAG_NO_TC_MEL 4096    /* n_fft = 512, n_mels <= 64: keep the mel projection on the CUDA cores (grouped walk)
+#define MMF_FLAG_NO_TC_MEL 4096    /* n_fft = 512, <= 112 non-empty bands: keep the mel projection on the CUDA cores (grouped walk)
                                       instead of the tcgen05.mma kind::f16 GEMM over 128-frame blocks (bf16 operand pairs,
                                       accumulators in tensor memory) */
 #define MMF_FLAG_FOLD_MFCC 128    /* composite calls: clamp + DCT-II inside the per-clip kernel even when delta is wanted

@@ -580,7 +580,8 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
 
   // mel projection as a tcgen05 GEMM (default where it applies; stft_mel_tc.cu)
   if (!(cfg->flags & (MMF_FLAG_NO_TC_MEL | MMF_FLAG_MEL_WALK | MMF_FLAG_MMA_MEL | MMF_FLAG_SPLIT_SMEM)) &&
-      stft_mel_tc_supported(cfg->n_fft, cfg->n_mels, cfg->hop_length, p->lead, p->packed)) {
+      stft_mel_tc_supported(cfg->n_fft, stft_mel_tc_active_bands(mel, cfg->n_mels, p->F), cfg->hop_length, p->lead,
+                            p->packed)) {
     std::vector<uint16_t> tab;
     uint16_t* d_t = nullptr;
     stft_mel_tc_table(mel, cfg->n_mels, p->F, tab);
@@ -589,6 +590,7 @@ int mmf_plan_create(mmf_plan** out, const mmf_config* cfg) {
       return cuda_fail(e, "uploading the tensor-core mel operand");
     }
     p->d_mel_tc = d_t;
+    p->mel_tc_act = stft_mel_tc_active_bands(mel, cfg->n_mels, p->F);
     // thread tau of a frame group holds samples 2 (tau + 16 n2), + 1: n2 selects a run of 32 samples
     p->win_lo = 16;
     p->win_hi = 0;
@@ -799,7 +801,7 @@ static int run_stft(mmf_plan* p, const float* pcm, int64_t n_clips, int64_t n_sa
   // the mel projection on the tensor cores wherever the plan supports it -- a decision of the configuration alone, so
   // that a clip's features never depend on the size or the chunking of the batch it came in
   if (p->d_mel_tc && logmel && !power && ((T + 127) / 128) * n_clips < 0x7fffffffLL) {
-    cudaError_t e = stft_mel_tc_launch(tmap, tma ? 1 : 0, pcm, n_clips, n_samples, clip_stride, (int)T, c.hop_length, p->lead, c.n_mels, c.amin,
+    cudaError_t e = stft_mel_tc_launch(tmap, tma ? 1 : 0, pcm, n_clips, n_samples, clip_stride, (int)T, c.hop_length, p->lead, c.n_mels, p->mel_tc_act, c.amin,
                                        c.preemph, p->d_window, p->win_lo, p->win_hi, p->d_tw1, p->d_mel_tc, logmel, clipmax, p->sm_count, st);
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "stft_mel_tc_kernel launch");

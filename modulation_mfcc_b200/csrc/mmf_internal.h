@@ -78,12 +78,13 @@ size_t stft_smem_bytes(int n_fft, int span_alloc, int span_bufs, int ppitch, int
 cudaError_t stft_mel_launch(int n_fft, const CUtensorMap& tmap, const StftArgs& a, int grid, size_t smem,
                             cudaStream_t st);
 
-// ---- K1 with the mel projection as a tcgen05 GEMM over 128-frame blocks (stft_mel_tc.cu; n_fft = 512, <= 64 bands)
-bool stft_mel_tc_supported(int n_fft, int n_mels, int hop, int lead, int packed);
+// ---- K1 with the mel projection as a tcgen05 GEMM over 128-frame blocks (stft_mel_tc.cu; n_fft = 512, <= 112 non-empty bands)
+int stft_mel_tc_active_bands(const std::vector<float>& mel, int n_mels, int F);
+bool stft_mel_tc_supported(int n_fft, int n_act, int hop, int lead, int packed);
 void stft_mel_tc_table(const std::vector<float>& mel, int n_mels, int F, std::vector<uint16_t>& tab);
 cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float* pcm, long n_clips, long n_samples,
                                long clip_stride, int T, int hop,
-                               int lead, int n_mels, float amin, float preemph, const float* window, int win_lo,
+                               int lead, int n_mels, int n_act, float amin, float preemph, const float* window, int win_lo,
                                int win_hi, const float2* tw1, const void* wtab, float* logmel, int* clipmax,
                                int sm_count, cudaStream_t st);
 
@@ -264,6 +265,7 @@ struct mmf_plan {
   int2* d_mg_step = nullptr;
   float4* d_mg_w = nullptr;
   int win_lo = 0, win_hi = 16;  // 32-sample groups of the zero-padded window (n_fft = 512) that are not all zero
+  int mel_tc_act = 0;        // non-empty mel bands (the rows of d_mel_tc)
   void* d_mel_tc = nullptr;  // bf16 [w1 ; w2] operand of the tcgen05 mel projection (null: not in use)
   float* d_dct = nullptr;  // [n_mels][nc_pad]
   float4* d_dct_bfrag = nullptr;  // DCT B fragments of the tensor-core MFCC kernel

@@ -6,12 +6,12 @@
 //   D[128 frames x n_mels] = P[128 x 272 bins] . W^T            (per block of 128 consecutive frames of a clip)
 //
 // issued as tcgen05.mma.cta_group::1.kind::f16 with BF16 operand pairs and FP32 accumulation in tensor memory:
-//   P = b1 + b2   (b1 = the top 16 bits of the fp32 power, b2 = the top 16 bits of the exact remainder),
+//   P = b1 + b2   (b1 = the fp32 power rounded to bf16, b2 = the top 16 bits of the exact remainder),
 //   W = w1 + w2   (round-to-nearest bf16 pair, built on the host),
 //   D1 = b1.w1,  D2 = b1.w2 + b2.w1  (the large and the small terms in separate accumulator columns; b2.w2 is
 //   below 2^-17 of the result), log-mel from D1 + D2.  bf16 keeps fp32's exponent range, so no per-frame scale is
 //   needed although the power spectrum of a frame spans many decades; the relative error of a mel power is below
-//   2^-15 (bound: tests/test_gpu_parity.py, north_star 1e-4).
+//   3e-5 (host emulation: tests/test_host.py; GPU bound: tests/test_gpu_parity.py, north_star 1e-4).
 //
 // One persistent 512-thread CTA per SM (16 warps; all 512 TMEM columns):
 //  * tile = 64 frames = one pass of the register FFT (32 half-warp groups x 2 frames, fft_regs.cuh / stft_core.cuh
@@ -165,6 +165,7 @@ struct StftTcArgs {
   int vec_ok;
   int win_lo, win_hi;       // 32-sample groups [win_lo, win_hi) of the zero-padded window that are not all zero
   int n_mels;
+  int n_act;                // bands [0, n_act) can be non-zero (the operand table covers them); [n_act, n_mels) are empty
   float amin;
   float preemph;
   const float* window;      // [512]
@@ -174,7 +175,7 @@ struct StftTcArgs {
   int* clipmax;
 };
 
-// NBQ = bands per epilogue warp = nb / 4 (nb = n_mels rounded up to 16)
+// NBQ = bands per epilogue warp = nb / 4 (nb = the non-empty bands n_act rounded up to 16)
 //
 // Thread organisation.  Warp w = 4 cg + q.  The four warps with the same q (they share an SM sub-partition and,
 // by the hardware's rule, the TMEM lane quarter q) form a GROUP: per tile the group transforms frames
@@ -185,7 +186,9 @@ struct StftTcArgs {
 // deliberate start stagger of up to 4000 cycles between the groups measured no different: DESIGN.md section 6a).
 // The only cross-group step is the MMA of a block: the last of the 16 warps to finish the block's transfers
 // issues it (nobody waits), and every warp picks the result up one transform later.
-template <int NBQ>
+// FAST160 = the bench / speech configuration (hop 160, TMA loader, no pre-emphasis) with the other load variants
+// compiled out: the tile loop loses four code paths and their run-time predicates.
+template <int NBQ, bool FAST160>
 __global__ void __launch_bounds__(kTcThreads, 1)
     stft_mel_tc_kernel(const __grid_constant__ CUtensorMap tmap, const StftTcArgs p) {
   using C = FftCfg<kNfft>;
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t wdesc = tc_desc(tc_smem_u32(s_w), 128, (uint32_t)(kTcKP / 8) * 128);
 
-  const int T = p.T, hop = p.hop, lead = p.lead;
+  const int T = p.T, hop = FAST160 ? 160 : p.hop, lead = FAST160 ? 0 : p.lead;
   const uint32_t n_boxes = (uint32_t)p.span_alloc / kBox;
 
   // block sequence of this CTA: blocks blockIdx.x, + gridDim.x, ...; 1 or 2 tiles of 64 frames per block
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float mx = -FLT_MAX;
     if (t < T) {
       float* dst = p.logmel + ((size_t)clip * p.n_mels + NBQ * cg) * T + t;
-      const int n_here = min(NBQ, p.n_mels - NBQ * cg);  // bands of this warp that exist
+      const int n_here = min(NBQ, p.n_act - NBQ * cg);  // bands of this warp that exist
       const float amin = p.amin;
 #pragma unroll
       for (int i = 0; i < NBQ; ++i) {
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   int clip = 0, t0b = 0;
   if (blk < p.n_blocks) {
     block_pos(blk, clip, t0b);
-    if (p.use_tma && cg == 0) issue_span(clip, t0b);
+    if ((FAST160 || p.use_tma) && cg == 0) issue_span(clip, t0b);
   }
   uint32_t tma_par = 0, mma_par = 0;
   bool have_prev = false;  // a block whose MMAs are issued (or about to be) and whose D has not been written out yet
@@ -354,31 +357,37 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2) wreg[n2] = s_win[tau + C::TPF * n2];
         const int off = shift + lead + f_own * hop;
-        if (p.use_tma) {
+        if constexpr (FAST160) {
           tc_mbar_wait(bar_tma, tma_par);
           tma_par ^= 1u;
+          ph_load_shared<kNfft, 5, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);  // shift == 0: spans start 16-byte aligned
         } else {
-          fill_span(clip, t0);  // (the previous tile's frames left the buffer before its first barrier)
-        }
-        if (p.preemph != 0.0f) {
-          const long n_valid = p.n_samples - ((long)(t0 + 16 * q + f_own) * hop - kNfft / 2);
-          ph_load_pre<kNfft>(v, span, off, hop, tau, wreg, p.preemph, n_valid);
-        } else if (hop == 160 && !(shift & 1)) {
-          ph_load_shared<kNfft, 5, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
-        } else if (hop == 128 && !(shift & 1)) {
-          ph_load_shared<kNfft, 4, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
-        } else if (hop == 256 && !(shift & 1)) {
-          ph_load_shared<kNfft, 8, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
-        } else if (p.vec_ok && !(shift & 1)) {
-          ph_load<kNfft, true>(v, span, off, hop, tau, wreg);
-        } else {
-          ph_load<kNfft, false>(v, span, off, hop, tau, wreg);
+          if (p.use_tma) {
+            tc_mbar_wait(bar_tma, tma_par);
+            tma_par ^= 1u;
+          } else {
+            fill_span(clip, t0);  // (the previous tile's frames left the buffer before its first barrier)
+          }
+          if (p.preemph != 0.0f) {
+            const long n_valid = p.n_samples - ((long)(t0 + 16 * q + f_own) * hop - kNfft / 2);
+            ph_load_pre<kNfft>(v, span, off, hop, tau, wreg, p.preemph, n_valid);
+          } else if (hop == 160 && !(shift & 1)) {
+            ph_load_shared<kNfft, 5, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
+          } else if (hop == 128 && !(shift & 1)) {
+            ph_load_shared<kNfft, 4, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
+          } else if (hop == 256 && !(shift & 1)) {
+            ph_load_shared<kNfft, 8, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
+          } else if (p.vec_ok && !(shift & 1)) {
+            ph_load<kNfft, true>(v, span, off, hop, tau, wreg);
+          } else {
+            ph_load<kNfft, false>(v, span, off, hop, tau, wreg);
+          }
         }
       }
       // the group's frames sit in registers: its span buffer is free, and its previous transfer (which read the
       // group's exchange buffers) is complete
       group_sync();
-      if (p.use_tma && cg == 0) {
+      if ((FAST160 || p.use_tma) && cg == 0) {
         if (j + 1 < n_tiles)
           issue_span(clip, t0 + kTcTF);
         else if (nblk < p.n_blocks)
@@ -424,14 +433,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int c = 0; c < 8; ++c) {
           const float4 x = *reinterpret_cast<const float4*>(tsrc + 4 * c);
           const float xs[4] = {x.x, x.y, x.z, x.w};
+          // b1 = the power rounded to bf16 (half an ulp added to the bits, top half kept), b2 = the top half of the
+          // exact, signed remainder.  Rounding b1 instead of truncating it halves |b2| and makes the neglected
+          // b2.w2 term and b2's own truncation zero-mean: worst mel-power error 5.0e-5 -> 2.9e-5 on the emulation
+          // (tests/test_host.py::test_bf16_pair_mel_projection_accuracy) for one more integer add per bin
+          uint32_t us[4];
           float ts[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) ts[e] = __uint_as_float(__float_as_uint(xs[e]) & 0xffff0000u);
+          for (int e = 0; e < 4; ++e) {
+            us[e] = __float_as_uint(xs[e]) + 0x8000u;
+            ts[e] = __uint_as_float(us[e] & 0xffff0000u);
+          }
           // exact remainders, two per packed subtract
           const pk r01 = ssub(pmake(xs[0], xs[1]), pmake(ts[0], ts[1])), r23 = ssub(pmake(xs[2], xs[3]), pmake(ts[2], ts[3]));
           const float rs[4] = {plo(r01), phi(r01), plo(r23), phi(r23)};
-          b1[2 * c] = __byte_perm(__float_as_uint(xs[0]), __float_as_uint(xs[1]), 0x7632);
-          b1[2 * c + 1] = __byte_perm(__float_as_uint(xs[2]), __float_as_uint(xs[3]), 0x7632);
+          b1[2 * c] = __byte_perm(us[0], us[1], 0x7632);
+          b1[2 * c + 1] = __byte_perm(us[2], us[3], 0x7632);
           b2[2 * c] = __byte_perm(__float_as_uint(rs[0]), __float_as_uint(rs[1]), 0x7632);
           b2[2 * c + 1] = __byte_perm(__float_as_uint(rs[2]), __float_as_uint(rs[3]), 0x7632);
         }
@@ -441,8 +458,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         uint32_t t1 = 0, t2 = 0;
         if (cg == 0 && hw == 0) {
           const float x = trow[256];
-          const float r = x - __uint_as_float(__float_as_uint(x) & 0xffff0000u);
-          t1 = __float_as_uint(x) >> 16;
+          const uint32_t u = __float_as_uint(x) + 0x8000u;
+          const float r = x - __uint_as_float(u & 0xffff0000u);
+          t1 = u >> 16;
           t2 = __float_as_uint(r) >> 16;
         }
         tc_tmem_st16x1(a_lane + 128 + 2 * cg, t1);
@@ -481,6 +499,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+// Bands without a single FFT bin (fmax above the Nyquist frequency: the reference's GUI default asks for 10 kHz at a
+// 10 kHz sampling rate, script/main.py:739) are not part of the GEMM: mel power 0 -> the amin floor, as librosa gives.
+__global__ void mel_empty_bands_kernel(float* __restrict__ logmel, int* __restrict__ clipmax, int T, int n_mels,
+                                       int n_act, float amin) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int clip = blockIdx.y;
+  const float db0 = 3.01029995663981195f * tc_log2(fmaxf(amin, 0.0f));
+  if (t < T)
+    for (int b = n_act; b < n_mels; ++b) logmel[((size_t)clip * n_mels + b) * T + t] = db0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(clipmax + clip, tc_float_key(db0));
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -496,10 +526,20 @@ static size_t tc_smem_bytes(int span_alloc, int nb) {
 // floats of the PCM span of one group (16 frames), whole TMA boxes
 int stft_mel_tc_span_alloc(int hop, int lead) { return (15 * hop + kNfft + lead + 3 + kBox - 1) / kBox * kBox; }
 
-// n_fft = 512 on the packed two-frame transform, up to 64 bands, tile span + tables within one SM's shared memory
-bool stft_mel_tc_supported(int n_fft, int n_mels, int hop, int lead, int packed) {
-  if (n_fft != kNfft || !packed || n_mels < 1 || n_mels > 64 || hop < 1) return false;
-  return tc_smem_bytes(stft_mel_tc_span_alloc(hop, lead), tc_nb(n_mels)) <= 227 * 1024;
+// bands [0, n_act) have at least one non-zero weight somewhere (trailing bands above the Nyquist frequency are empty)
+int stft_mel_tc_active_bands(const std::vector<float>& mel, int n_mels, int F) {
+  int n_act = 1;
+  for (int m = 0; m < n_mels; ++m)
+    for (int k = 0; k < F; ++k)
+      if (mel[(size_t)m * F + k] != 0.0f) n_act = m + 1;
+  return n_act;
+}
+
+// n_fft = 512 on the packed two-frame transform; the non-empty bands (rounded up to 16) must leave A (272 columns)
+// and D (2 nb columns) inside the 512 TMEM columns, and the tile spans + tables inside one SM's shared memory
+bool stft_mel_tc_supported(int n_fft, int n_act, int hop, int lead, int packed) {
+  if (n_fft != kNfft || !packed || n_act < 1 || tc_nb(n_act) > 112 || hop < 1) return false;
+  return tc_smem_bytes(stft_mel_tc_span_alloc(hop, lead), tc_nb(n_act)) <= 227 * 1024;
 }
 
 static uint16_t bf16_rn_bits(float f) {
@@ -518,6 +558,7 @@ static float bf16_to_float(uint16_t b) {
 // mel: dense [n_mels][F] filterbank (host_mel_dense).  tab: 2 nb rows x 272 bf16, canonical no-swizzle K-major
 // ((row / 8) * (272 / 8) + k / 8) * 64 + (row % 8) * 8 + k % 8; rows [0, nb) = w1 of band row, rows [nb, 2 nb) = w2
 void stft_mel_tc_table(const std::vector<float>& mel, int n_mels, int F, std::vector<uint16_t>& tab) {
+  n_mels = stft_mel_tc_active_bands(mel, n_mels, F);  // rows of the table = non-empty bands
   const int nb = tc_nb(n_mels);
   tab.assign((size_t)2 * nb * kTcKP, 0);
   auto idx = [&](int row, int k) { return ((size_t)(row / 8) * (kTcKP / 8) + k / 8) * 64 + (row % 8) * 8 + k % 8; };
@@ -533,7 +574,7 @@ void stft_mel_tc_table(const std::vector<float>& mel, int n_mels, int F, std::ve
 
 cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float* pcm, long n_clips, long n_samples,
                                long clip_stride, int T, int hop,
-                               int lead, int n_mels, float amin, float preemph, const float* window, int win_lo,
+                               int lead, int n_mels, int n_act, float amin, float preemph, const float* window, int win_lo,
                                int win_hi, const float2* tw1, const void* wtab, float* logmel, int* clipmax,
                                int sm_count, cudaStream_t st) {
   StftTcArgs a{};
@@ -554,6 +595,7 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
   a.lead = lead;
   a.vec_ok = (hop % 2 == 0) ? 1 : 0;
   a.n_mels = n_mels;
+  a.n_act = n_act;
   a.amin = amin;
   a.preemph = preemph;
   a.window = window;
@@ -561,14 +603,21 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
   a.wtab = reinterpret_cast<const uint16_t*>(wtab);
   a.logmel = logmel;
   a.clipmax = clipmax;
-  const int nb = tc_nb(n_mels);
+  const int nb = tc_nb(n_act);
   const size_t smem = tc_smem_bytes(a.span_alloc, nb);
   const unsigned grid = (unsigned)std::min<long>((long)a.n_blocks, (long)sm_count);
+  const bool fast160 = hop == 160 && use_tma && preemph == 0.0f && lead == 0;
 #define MMF_TCMEL_CASE(NBQ)                                        \
   case NBQ: {                                                      \
-    auto kfn = stft_mel_tc_kernel<NBQ>;                            \
-    MMF_SMEM_ONCE(kfn, 227 * 1024);                                \
-    kfn<<<grid, kTcThreads, smem, st>>>(tmap, a);                  \
+    if (fast160) {                                                 \
+      auto kfn = stft_mel_tc_kernel<NBQ, true>;                    \
+      MMF_SMEM_ONCE(kfn, 227 * 1024);                              \
+      kfn<<<grid, kTcThreads, smem, st>>>(tmap, a);                \
+    } else {                                                       \
+      auto kfn = stft_mel_tc_kernel<NBQ, false>;                   \
+      MMF_SMEM_ONCE(kfn, 227 * 1024);                              \
+      kfn<<<grid, kTcThreads, smem, st>>>(tmap, a);                \
+    }                                                              \
     break;                                                         \
   }
   switch (nb / 4) {
@@ -576,10 +625,23 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
     MMF_TCMEL_CASE(8)
     MMF_TCMEL_CASE(12)
     MMF_TCMEL_CASE(16)
+    MMF_TCMEL_CASE(20)
+    MMF_TCMEL_CASE(24)
+    MMF_TCMEL_CASE(28)
     default: return cudaErrorInvalidValue;
   }
 #undef MMF_TCMEL_CASE
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && n_act < n_mels) {
+    for (long c0 = 0; c0 < n_clips && e == cudaSuccess; c0 += 65535) {
+      const unsigned nc = (unsigned)std::min<long>(65535, n_clips - c0);
+      mel_empty_bands_kernel<<<dim3((unsigned)((T + 255) / 256), nc), 256, 0, st>>>(
+          logmel + (size_t)c0 * n_mels * T, clipmax + c0, T, n_mels, n_act, amin);
+      count_launch();
+      e = cudaGetLastError();
+    }
+  }
+  return e;
 }
 
 }  // namespace mmf

@@ -971,6 +971,10 @@ TC_MEL_CASES = {
     "mel26_8k": (8000, 0.03, 0.0125, 26, 0.0, 4000.0, 2.5, 0.0),
     "mel13_oddhop": (16000, 0.02, 0.0100625, 13, 0.0, 8000.0, 2.0, 0.0),  # hop 161: scalar span loads
     "mel40_preemph": (16000, 0.025, 0.01, 40, 0.0, 8000.0, 2.0, 0.97),
+    # the reference GUI's default (script/main.py:739): 128 bands up to 10 kHz at a 10 kHz sampling rate -- the bands
+    # above the Nyquist frequency are empty, 100 remain: 112 accumulator columns per term
+    "gui_default_128": (10000, 0.025, 0.005, 128, 100.0, 10000.0, 2.0, 0.0),
+    "mel96_fmax_low": (16000, 0.025, 0.01, 96, 0.0, 6000.0, 1.5, 0.0),
 }
 
 

@@ -454,3 +454,50 @@ def test_hq_resampler_is_transparent_below_the_band_edge(sr_in, sr_out):
     h, n_pre, n_out = design_resample_filter(len(x), up, down, "scipy")
     mine = scipy.signal.upfirdn(h.astype(np.float64), x, up, down)[n_pre : n_pre + n_out]
     assert np.max(np.abs(mine - scipy.signal.resample_poly(x, up, down))) < 2e-6
+
+
+def test_bf16_pair_mel_projection_accuracy():
+    """Host emulation of the operand format of K1's tcgen05 mel projection (csrc/stft_mel_tc.cu): power = b1 + b2
+    (the fp32 value rounded half-up to bf16 -- half an ulp added to the bits, top half kept, as the kernel does --
+    and the top 16 bits of the exact remainder), weights
+    = w1 + w2 (round-to-nearest bf16 pair), D = b1.w1 + (b1.w2 + b2.w1) accumulated in fp32.  On the oracle's own power
+    spectra the mel powers stay within 3.5e-5 of the float64 projection (north_star bound 1e-4); a single bf16 operand
+    (no b2 / w2) misses the bound by two decades, which is why the kernel carries the pair."""
+    sr = 16000
+    rng = np.random.default_rng(5)
+    worst_pair, worst_single = 0.0, 0.0
+    for n_mels, fmax in ((40, 8000.0), (64, 7600.0), (128, 8000.0)):
+        y = mm_synth(rng, sr)
+        _, inter = oracle.mfcc(y, sr, n_mfcc=13, win_length=400, hop_length=160, n_fft=512, fmin=0.0, fmax=fmax, n_mels=n_mels,
+                               return_intermediates=True)
+        P = inter["power"].astype(np.float32)              # [257, T]
+        W = oracle.mel_filterbank(sr, 512, n_mels, 0.0, fmax).astype(np.float32)  # [n_mels, 257]
+        ref = W.astype(np.float64) @ P.astype(np.float64)
+
+        def trunc16(x):
+            return (x.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+
+        def rn16(x):
+            u = x.view(np.uint32).astype(np.uint64)
+            u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+            return u.astype(np.uint32).view(np.float32)
+
+        b1 = trunc16((P.view(np.uint32) + np.uint32(0x8000)).view(np.float32))
+        b2 = trunc16(P - b1)
+        w1 = rn16(W)
+        w2 = rn16(W - w1)
+        d1 = w1 @ b1                                        # fp32 accumulation, like the tensor core's
+        d2 = w2 @ b1 + w1 @ b2
+        got = (d1 + d2).astype(np.float64)
+        floor = ref.max() * 1e-8                            # the top_db = 80 clamp floor of the clip
+        ok = ref > floor
+        worst_pair = max(worst_pair, float(np.max(np.abs(got - ref)[ok] / ref[ok])))
+        worst_single = max(worst_single, float(np.max(np.abs((w1 @ b1).astype(np.float64) - ref)[ok] / ref[ok])))
+    assert worst_pair < 3.5e-5, worst_pair
+    assert worst_single > 1e-3, worst_single
+
+
+def mm_synth(rng, sr):
+    t = np.arange(2 * sr) / sr
+    y = 0.1 * rng.standard_normal(t.size) + 0.3 * np.sin(2 * np.pi * (200 + 50 * np.sin(2 * np.pi * 3 * t)) * t) * (0.6 + 0.4 * np.sin(2 * np.pi * 4 * t))
+    return np.clip(y, -1, 1).astype(np.float32)
