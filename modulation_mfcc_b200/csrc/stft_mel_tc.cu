@@ -360,7 +360,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if constexpr (FAST160) {
           tc_mbar_wait(bar_tma, tma_par);
           tma_par ^= 1u;
-          ph_load_shared<kNfft, 5, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);  // shift == 0: spans start 16-byte aligned
+          // (shift == 0: the spans start 16-byte aligned.)  The 25 ms window of speech front ends (400 of 512) as
+          // compile-time bounds: the 21 load predicates of the generic form disappear
+          if (p.win_lo == 1 && p.win_hi == 15)
+            ph_load_shared<kNfft, 5, true>(v, span, off, tau, wreg, 1, 15);
+          else
+            ph_load_shared<kNfft, 5, true>(v, span, off, tau, wreg, p.win_lo, p.win_hi);
         } else {
           if (p.use_tma) {
             tc_mbar_wait(bar_tma, tma_par);
