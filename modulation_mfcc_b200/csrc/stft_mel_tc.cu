@@ -197,8 +197,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr uint32_t kDCol = 2 * kTcACols;  // D1 at kDCol, D2 at kDCol + NB
   static_assert(2 * kTcACols + 2 * NB <= 512, "A (b1, b2) and D (D1, D2) must fit the 512 TMEM columns");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // hop 160 without pre-emphasis: 15 * 160 + 512 + 3 samples -> 3072 floats per group span, a compile-time constant
+  // in the fast instantiation (every shared-memory offset below then folds into an immediate)
+  const int span_alloc = FAST160 ? 3072 : p.span_alloc;
   float* s_span = reinterpret_cast<float*>(smem_raw);                           // [4][span_alloc]
-  pk* s_xb = reinterpret_cast<pk*>(s_span + 4 * p.span_alloc);                  // [32][kTcXS]
+  pk* s_xb = reinterpret_cast<pk*>(s_span + 4 * span_alloc);                    // [32][kTcXS]
   uint16_t* s_w = reinterpret_cast<uint16_t*>(s_xb + kTcSlots * kTcXS);         // [2 NB x 272] bf16
   c2* s_tw1 = reinterpret_cast<c2*>(s_w + 2 * NB * kTcKP);                      // [256]
   float2* s_win = reinterpret_cast<float2*>(s_tw1 + C::TW1);                    // [256] half-scaled window pairs
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const float* trow = reinterpret_cast<const float*>(s_xb + tbi * kTcXS) + (tbi & 1) * kTcOddShift + (tfr & 1) * kTcRowB;
   const float* tsrc = trow + 64 * cg + 32 * hw;
   const uint32_t lane_q = (uint32_t)(32 * q) << 16;
-  float* span = s_span + q * p.span_alloc;
+  float* span = s_span + q * span_alloc;
   uint64_t* bar_tma = &s_bar[q];
   uint64_t* bar_mma = &s_bar[4];
   auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); };
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint64_t wdesc = tc_desc(tc_smem_u32(s_w), 128, (uint32_t)(kTcKP / 8) * 128);
 
   const int T = p.T, hop = FAST160 ? 160 : p.hop, lead = FAST160 ? 0 : p.lead;
-  const uint32_t n_boxes = (uint32_t)p.span_alloc / kBox;
+  const uint32_t n_boxes = (uint32_t)span_alloc / kBox;
 
   // block sequence of this CTA: blocks blockIdx.x, + gridDim.x, ...; 1 or 2 tiles of 64 frames per block
   auto block_pos = [&](unsigned blk, int& clip, int& t0) {
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int g0 = ((t0 + 16 * q) * hop - kNfft / 2 - lead) & ~3;  // 16-byte aligned start (remainder: `shift`)
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_mbar_expect_tx(bar_tma, (uint32_t)p.span_alloc * 4u);
+      tc_mbar_expect_tx(bar_tma, (uint32_t)span_alloc * 4u);
     }
     __syncwarp();
     for (uint32_t bx = lane; bx < n_boxes; bx += 32) tc_tma_load_2d(span + bx * kBox, &tmap, g0 + (int)bx * kBox, clip, bar_tma);
@@ -333,8 +336,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   unsigned blk = blockIdx.x;
   int clip = 0, t0b = 0;
+  // (clip, first frame) of this CTA's next block advance by gridDim.x blocks without dividing again
+  const unsigned step_q = gridDim.x / p.blocks_per_clip, step_r = gridDim.x - step_q * p.blocks_per_clip;
+  unsigned bin = 0;  // block index within the clip
   if (blk < p.n_blocks) {
     block_pos(blk, clip, t0b);
+    bin = (unsigned)t0b / kTcBlock;
     if ((FAST160 || p.use_tma) && cg == 0) issue_span(clip, t0b);
   }
   uint32_t tma_par = 0, mma_par = 0;
@@ -344,8 +351,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   while (blk < p.n_blocks) {
     const int n_tiles = (t0b + kTcTF < T) ? 2 : 1;
     const unsigned nblk = blk + gridDim.x;
-    int nclip = 0, nt0b = 0;
-    if (nblk < p.n_blocks) block_pos(nblk, nclip, nt0b);
+    int nclip = clip + (int)step_q;
+    unsigned nbin = bin + step_r;
+    if (nbin >= p.blocks_per_clip) {
+      nbin -= p.blocks_per_clip;
+      ++nclip;
+    }
+    const int nt0b = (int)nbin * kTcBlock;
     for (int j = 0; j < n_tiles; ++j) {
       const int t0 = t0b + kTcTF * j;
       const int g_first = (t0 + 16 * q) * hop - kNfft / 2 - lead;
@@ -491,6 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     pt0 = t0b;
     blk = nblk;
     clip = nclip;
+    bin = nbin;
     t0b = nt0b;
   }
   // ---------------- drain: epilogue of the last block
@@ -611,7 +624,7 @@ cudaError_t stft_mel_tc_launch(const CUtensorMap& tmap, int use_tma, const float
   const int nb = tc_nb(n_act);
   const size_t smem = tc_smem_bytes(a.span_alloc, nb);
   const unsigned grid = (unsigned)std::min<long>((long)a.n_blocks, (long)sm_count);
-  const bool fast160 = hop == 160 && use_tma && preemph == 0.0f && lead == 0;
+  const bool fast160 = hop == 160 && use_tma && preemph == 0.0f && lead == 0 && a.span_alloc == 3072;
 #define MMF_TCMEL_CASE(NBQ)                                        \
   case NBQ: {                                                      \
     if (fast160) {                                                 \
