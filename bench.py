@@ -559,7 +559,7 @@ def run_b200(args):
     except Exception:
         pass
     tc_mel = not (int(os.environ.get("MMF_FLAGS", "0")) & (4096 | 2048 | 16 | 2))
-    k1_name = ("stft_mel_tc_kernel<12> (fused frame/window/rFFT/|X|^2 on packed FP32 + mel projection as a tcgen05 bf16x2 "
+    k1_name = ("stft_mel_tc_kernel<12, 1> (fused frame/window/rFFT/|X|^2 on packed FP32 + mel projection as a tcgen05 bf16x2 "
                "GEMM over 128-frame blocks + log)") if tc_mel else "stft_mel_kernel<512, c2> (fused frame/window/rFFT/|X|^2/mel/log)"
     # the mel GEMM inside K1: per 128-frame block 17 K-slabs x {M128 N96 K16, M128 N48 K16} MMAs (bf16 operand pairs)
     mel_gemm_flops = CLIPS * ((T + 127) // 128) * 17 * (2 * 128 * 96 * 16 + 2 * 128 * 48 * 16) if tc_mel else 0

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kMfccThreads)
   __syncthreads();
 
   const long clip = blockIdx.y;
+  const int Ti = (int)T;  // row pitch as a 32-bit value: u * Ti is one IMAD.WIDE per address instead of a 64-bit product
   const int halo = delta != nullptr ? 1 : 0;
   const int per_block = kMfccThreads - 2 * halo;
   const long t = (long)blockIdx.x * per_block - halo + tid;
@@ -149,21 +150,21 @@ __global__ void __launch_bounds__(kMfccThreads)
   float* col = logmel + (size_t)clip * n_mels * T + tc;
   const bool store_clamped = clamp_in_place && own;
   {
-    const size_t T8 = (size_t)8 * T;
+    const int T8 = 8 * Ti;
     float cur[8], nxt[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) cur[u] = __ldcs(col + (size_t)u * T);
+    for (int u = 0; u < 8; ++u) cur[u] = __ldcs(col + u * Ti);
     const float* s_row = s_dct;
     for (int m0 = 0; m0 < n_mels; m0 += 8) {
       float* nrow = col + T8;
       if (m0 + 8 < n_mels) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) nxt[u] = __ldcs(nrow + (size_t)u * T);
+        for (int u = 0; u < 8; ++u) nxt[u] = __ldcs(nrow + u * Ti);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float x = fmaxf(cur[u], thr);
-        if (store_clamped) col[(size_t)u * T] = x;
+        if (store_clamped) col[u * Ti] = x;
         const pk xx = pmake(x, x);
         const float4* d4 = reinterpret_cast<const float4*>(s_row + 16 * u);
 #pragma unroll
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kMfccThreads)
 #pragma unroll
     for (int j = 0; j < 2 * NP; ++j) {
       if (j < n_mfcc) *dst = out[j];
-      dst += T;
+      dst += Ti;
     }
   }
   if (delta != nullptr) {
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kMfccThreads)
           // (c[1] - c[-1]) / 2 and (c[1] - c[0]) / 1 exactly as mfcc_kernel: division by 2 = multiplication by 0.5
           *dst = T == 1 ? 0.0f : (c[hi] - c[lo]) * scale;
         }
-        dst += T;
+        dst += Ti;
       }
     }
   }
@@ -223,7 +224,7 @@ cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const i
   dim3 grid((unsigned)((T + per_block - 1) / per_block), (unsigned)n_clips);
   int nc = n_mfcc <= 16 ? 16 : (n_mfcc <= 32 ? 32 : (n_mfcc <= 64 ? 64 : 128));
   size_t smem = ((size_t)n_mels * nc + (size_t)nc * (kMfccThreads + 1)) * sizeof(float);
-  if (nc == 16 && nc_pad == 16 && n_mels % 8 == 0 && n_mels >= 8) {
+  if (nc == 16 && nc_pad == 16 && n_mels % 8 == 0 && n_mels >= 8 && T < (1L << 27)) {
     const int np = n_mfcc <= 8 ? 4 : (n_mfcc + 1) / 2;
 #define MMF_MFCC_PK_CASE(N)                                                                                        \
   case N: {                                                                                                        \
