@@ -1183,7 +1183,12 @@ static int features_host_impl(mmf_plan* plan, const void* pcm_host_v, int pcm16,
   const bool need_mfcc_dev = mfcc_host || want_mod;
   // chunk the batch so that H2D of chunk i+1 overlaps compute of chunk i (two streams, two slots)
   const size_t clip_bytes = (size_t)n_samples * 4;
-  int64_t chunk = std::max<int64_t>(1, (int64_t)((48u << 20) / clip_bytes));
+  // chunk size in bytes of float32 PCM on the device, from a sweep on B200 (bench e2e legs, 1024 x 10 s clips):
+  // float32 host input 8 / 16 / 24 / 32 / 48 / 96 MB -> 0.68 / 0.81 / 0.82 / 0.82 / 0.81 / 0.80 M audio-s/s (small
+  // chunks pay launch + copy set-up, large ones a longer unoverlapped head and tail); int16 host input moves half
+  // the bytes per clip and keeps gaining up to 96 MB (0.94 / 1.16 / 1.25 / 1.34 / 1.37 / 1.44 M)
+  const size_t chunk_bytes = pcm16 ? (96u << 20) : (32u << 20);
+  int64_t chunk = std::max<int64_t>(1, (int64_t)(chunk_bytes / clip_bytes));
   chunk = std::min<int64_t>(chunk, n_clips);
   const size_t pcm_slot = align_up((size_t)chunk * n_samples * 4, 256);
   const size_t tot_slot = align_up((size_t)chunk * T * 8, 256);

@@ -588,10 +588,10 @@ def test_full_size_properties(cuda_device):
 
 
 def test_host_path_multi_chunk_equals_device_path(cuda_device):
-    """The e2e entry point the bench times (``mmf_features_host``: 48 MB chunks over two streams and two
-    workspace slots) over 4 chunks, float32 and int16, against the device-resident call and the oracle."""
+    """The e2e entry point the bench times (``mmf_features_host``: 32 MB chunks over two streams and two
+    workspace slots) over 5 chunks (float32) / 2 chunks (int16), against the device-resident call and the oracle."""
     torch = _torch()
-    sr, n, B = 16000, 160000, 256  # 78 clips per chunk -> 4 chunks, the last one ragged
+    sr, n, B = 16000, 160000, 256  # 52 clips per chunk -> 5 chunks (int16: 157 -> 2), the last one ragged
     pcm = mm.synth_batch_device(B, n, sr, seed=4321, device=cuda_device)
     fx = mm.FeatureExtractor(sr, tStep=0.01, winLen=0.025, n_fft=512, n_mels=40, n_mfcc=13)
     dev = fx(pcm, want_logmel=False)
@@ -606,12 +606,12 @@ def test_host_path_multi_chunk_equals_device_path(cuda_device):
     for k in want:
         assert np.array_equal(out2[k], out[k][100:180]), k
         assert torch.equal(dev2[k], dev[k][:64]), k
-    for i in (0, 77, 78, 233, 255):  # both sides of a chunk boundary, first and last clip
+    for i in (0, 51, 52, 233, 255):  # both sides of a chunk boundary, first and last clip
         ref = oracle.mfcc_features(host_in[i], sr)
         assert np.max(np.abs(out["mfcc"][i] - ref["mfcc"])) < ABS_TOL
         assert np.max(np.abs(out["totChange"][i] - ref["totChange"])) < ABS_TOL
         assert np.max(np.abs(out["modspec"][i] - ref["modspec"])) < ABS_TOL
-    # int16 ingest: same chunking, samples scaled by 1/32768 on the device
+    # int16 ingest: 96 MB chunks (157 clips), samples scaled by 1/32768 on the device
     q = torch.clamp(torch.round(pcm * 32768.0), -32768, 32767).to(torch.int16)
     out16 = fx.host_call(q.cpu().numpy(), want=want)
     devq = fx(q.to(torch.float32) / 32768.0, want_logmel=False)
