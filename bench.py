@@ -642,7 +642,7 @@ def run_b200(args):
                 "achieved_tflops": mel_gemm_flops / (k1 * 1e-3) / 1e12,
                 "peak_tflops": float(peaks.get("bf16_tflops", 1680.0)),
                 "frac": mel_gemm_flops / (k1 * 1e-3) / 1e12 / float(peaks.get("bf16_tflops", 1680.0)),
-                "note": "the GEMM is 4 % of the kernel's work and runs underneath the transform; ncu: tensor pipe 5.5 % active",
+                "note": "the GEMM is 4 % of the kernel's work and runs underneath the transform; ncu: tensor pipe 6 % active",
             } if tc_mel else None,
         },
         "roofline_k6": {
