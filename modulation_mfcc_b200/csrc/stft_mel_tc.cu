@@ -13,7 +13,8 @@
 //   needed although the power spectrum of a frame spans many decades; the relative error of a mel power is below
 //   3e-5 (host emulation: tests/test_host.py; GPU bound: tests/test_gpu_parity.py, north_star 1e-4).
 //
-// One persistent 512-thread CTA per SM (16 warps; all 512 TMEM columns):
+// One persistent 512-thread CTA per SM (16 warps; all 512 TMEM columns), organised as four independent 4-warp groups
+// (see the kernel's own comment); bands [0, n_act) with at least one FFT bin (n_act rounded up to 16 <= 112):
 //  * tile = 64 frames = one pass of the register FFT (32 half-warp groups x 2 frames, fft_regs.cuh / stft_core.cuh
 //    exactly as in stft_mel.cu), PCM span by TMA; two tiles make one block of 128 frames = the M of the MMA;
 //  * the split step leaves each group's two power rows ([frame][bin], fp32) in the group's OWN exchange buffer,
@@ -22,8 +23,8 @@
 //    with tcgen05.st.16x32bx2 (16 TMEM lanes per instruction: tile j of a block owns lanes 16 j .. 16 j + 15 of
 //    every 32-lane quarter, so all 16 warps take part in every tile -- the 32-lane shape would leave half of them
 //    idle; addressing and packing order checked by tools/ubench/tmem_st16.cu), splitting b1 / b2 on the way
-//    (two byte permutes, one AND and one subtract per bin);
-//  * after the second tile one thread issues the 34 MMAs (17 K slabs x {N = 2 nb against [w1 | w2], N = nb against
+//    (one integer add, one AND, half a packed subtract and one byte permute per bin);
+//  * after the second tile the last warp to finish issues the 34 MMAs (17 K slabs x {N = 2 nb against [w1 | w2], N = nb against
 //    w1}) and commits to an mbarrier; they run underneath the next tile's transform;
 //  * epilogue (before the next block's first transfer): tcgen05.ld of D1, D2 (lane = frame), log, coalesced stores
 //    along time, warp-shuffle max -> atomicMax per clip.
