@@ -35,7 +35,8 @@ namespace mmf {
 
 namespace {
 
-constexpr int kMtThreads = 128;
+constexpr int kMtRows = 128;      // rows (trajectory windows) per block = the M of the MMA
+constexpr int kMtThreads = 256;   // two threads per row: K halves in the operand preparation, bin halves in the epilogue
 constexpr int kMtKMax = 128;  // win <= 128
 constexpr long kMtSmemLimit = 110 * 1024;  // dynamic shared memory per CTA (two CTAs per SM)
 
@@ -114,7 +115,7 @@ struct ModTcArgs {
 // half h, slot j (0..63): j < 32 -> Re X[32 h + j]; j >= 32 -> Im X[32 h + j - 32], except (h = 0, j = 32),
 // whose Im X[0] = 0 slot carries Re X[nfft / 2]
 template <int NFFT, int KS>
-__global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs p) {
+__global__ void __launch_bounds__(kMtThreads, 2) modspec_tc_kernel(const ModTcArgs p) {
   static_assert(NFFT == 128, "two halves of 32 bins");
   constexpr int nb = NFFT / 2 + 1;  // odd: conflict-free row pitch of the staging buffer
   constexpr int H = NFFT / 2;
@@ -123,13 +124,17 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
   __half* sGh = reinterpret_cast<__half*>(sm_mt);
   __half* sGl = reinterpret_cast<__half*>(sm_mt + g_bytes);
   float* s_buf = reinterpret_cast<float*>(sm_mt + 2 * g_bytes);          // [128][nb]: trajectories, then |X|^2 rows
-  float** s_dst = reinterpret_cast<float**>(s_buf + kMtThreads * nb);    // [128] output row pointers (128 * nb * 4 bytes: 8-byte aligned)
-  float* s_iband = reinterpret_cast<float*>(s_dst + kMtThreads);         // [wc * n_coef][n_bands]
+  float** s_dst = reinterpret_cast<float**>(s_buf + kMtRows * nb);       // [128] output row pointers (128 * nb * 4 bytes: 8-byte aligned)
+  float* s_iband = reinterpret_cast<float*>(s_dst + kMtRows);            // [wc * n_coef][n_bands]
+  __shared__ float s_part[2][kMtRows];  // the two halves of a row's sum, then of its maximum
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t tmem_base;
   __shared__ int s_blo[16], s_bhi[16];
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  // thread -> (row of the block, half): warps 0-3 and 4-7 own the same four TMEM lane quarters (warp & 3), so the two
+  // threads of a row sit in warps w and w + 4 and can both reach the row's lane
+  const int rr = tid & (kMtRows - 1), half = tid >> 7;
 
   for (int i = tid; i < 2 * g_bytes / 16; i += kMtThreads)
     reinterpret_cast<uint4*>(sm_mt)[i] = reinterpret_cast<const uint4*>(p.g)[i];
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t d_tm = tmem_base, ah_tm = tmem_base + NFFT, al_tm = ah_tm + kMtKMax / 2;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t bar_a = mt_smem_u32(&bar);
   uint32_t parity = 0;
   const uint32_t sbo = (uint32_t)(p.kp / 8) * 128;
@@ -173,17 +178,17 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
   const int wca = (int)min((long)p.wc, p.n_win - w0);
   const int n_items = wca * p.n_coef;
   const int span = (wca - 1) * p.hop + p.win;
-  for (int r0 = 0; r0 < n_items; r0 += kMtThreads) {
+  for (int r0 = 0; r0 < n_items; r0 += kMtRows) {
     // ---- stage the trajectories this row block touches (coefficients c_lo .. c_hi), coalesced
-    const int c_lo = r0 / wca, c_hi = min(r0 + kMtThreads - 1, n_items - 1) / wca;
+    const int c_lo = r0 / wca, c_hi = min(r0 + kMtRows - 1, n_items - 1) / wca;
     // whole clip in one chunk and the touched trajectories fit with their own pitch T: one flat copy
     const int n_tr = c_hi - c_lo + 1;
-    const bool flat_in = wca == p.n_win && (long)n_tr * p.T <= (long)kMtThreads * nb;
+    const bool flat_in = wca == p.n_win && (long)n_tr * p.T <= (long)kMtRows * nb;
     const int pitch = flat_in ? (int)p.T : span;
     if (flat_in) {
       const float* src0 = p.mfcc + ((size_t)clip * p.n_coef + c_lo) * p.T;
       const int total = (n_tr - 1) * (int)p.T + span;
-      constexpr int kBatch = 33;  // 2 x 33 x 128 >= 128 * nb
+      constexpr int kBatch = 17;  // 2 x 17 x 256 >= 128 * nb
       for (int e0 = 0; e0 < total; e0 += kBatch * kMtThreads) {
         float a[kBatch];
 #pragma unroll
@@ -234,59 +239,71 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
       }
     }
     __syncthreads();
-    // ---- one row per thread: mean removal, power-of-two scale, fp16 split, A into tensor memory
-    const int r = r0 + tid;
+    // ---- two threads per row (K slabs [0, KH) and [KH, KS)): mean removal, power-of-two scale, fp16 split, A into
+    // tensor memory.  The row's sum and maximum are combined through shared memory (same order in both threads).
+    const int r = r0 + rr;
     const bool valid = r < n_items;
     const int coef = valid ? r / wca : c_lo;
     const int w = valid ? r - coef * wca : 0;
     float inv_s = 1.0f;
     {
+      constexpr int KH = (KS + 1) / 2;          // slabs of half 0
+      constexpr int KL = KH;                    // slabs held per thread (half 1 may use one fewer)
+      const int ks0 = half == 0 ? 0 : KH, nks = half == 0 ? KH : KS - KH;
       const float* x = s_buf + (coef - c_lo) * pitch + w * p.hop;
-      constexpr int KP = 16 * KS;
-      float v[KP];
+      float v[16 * KL];
       // mean removal relative to a pivot (the window's first sample): the differences are small next to a
       // trajectory's offset (c0 sits near -500), so the fp32 sum loses far less; four partial sums
-      // rows past the last item read row (c_lo, 0): finite data, results never stored.  win > 16 (KS - 1):
-      // only the last slab needs the k < win predicate
+      // rows past the last item read row (c_lo, 0): finite data, results never stored
       const float pivot = x[0];
       float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        v[k] = (k < KP - 16 || k < p.win) ? x[k] - pivot : 0.0f;
-        sum4[k & 3] += v[k];
+      for (int kl = 0; kl < 16 * KL; ++kl) {
+        const int k = 16 * ks0 + kl;
+        v[kl] = (kl < 16 * nks && k < p.win) ? x[k] - pivot : 0.0f;
+        sum4[kl & 3] += v[kl];
       }
-      const float mean = ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) * inv_win;
+      s_part[half][rr] = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      __syncthreads();
+      const float mean = (s_part[0][rr] + s_part[1][rr]) * inv_win;
+      __syncthreads();  // both halves have read the sums: the buffer takes the maxima
       float m = 0.0f;
 #pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        v[k] = (k < KP - 16 || k < p.win) ? v[k] - mean : 0.0f;
-        m = fmaxf(m, fabsf(v[k]));
+      for (int kl = 0; kl < 16 * KL; ++kl) {
+        const int k = 16 * ks0 + kl;
+        v[kl] = (kl < 16 * nks && k < p.win) ? v[kl] - mean : 0.0f;
+        m = fmaxf(m, fabsf(v[kl]));
       }
+      s_part[half][rr] = m;
+      __syncthreads();
+      m = fmaxf(s_part[0][rr], s_part[1][rr]);
       int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
       if (m < 1e-30f) e = 5;
       e = max(-100, min(100, e));
       const float s = __uint_as_float((uint32_t)(5 - e + 127) << 23);  // m s in [32, 64)
       inv_s = __uint_as_float((uint32_t)(e - 5 + 127) << 23);
 #pragma unroll
-      for (int kc = 0; kc < KS; ++kc) {
-        uint32_t hi[8], lo[8];
+      for (int kc = 0; kc < KL; ++kc) {
+        if (kc < nks) {  // (warp-uniform: a warp lies in one half)
+          uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = v[16 * kc + 2 * j] * s, b = v[16 * kc + 2 * j + 1] * s;
-          const __half2 h2 = __floats2half2_rn(a, b);  // a in the low half = element 2j of the column
-          const float2 f2 = __half22float2(h2);
-          const __half2 l2 = __floats2half2_rn((a - f2.x) * 2048.0f, (b - f2.y) * 2048.0f);
-          hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+          for (int j = 0; j < 8; ++j) {
+            const float a = v[16 * kc + 2 * j] * s, b = v[16 * kc + 2 * j + 1] * s;
+            const __half2 h2 = __floats2half2_rn(a, b);  // a in the low half = element 2j of the column
+            const float2 f2 = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn((a - f2.x) * 2048.0f, (b - f2.y) * 2048.0f);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          mt_tmem_st8(ah_tm + lane_base + 8 * (ks0 + kc), hi);
+          mt_tmem_st8(al_tm + lane_base + 8 * (ks0 + kc), lo);
         }
-        mt_tmem_st8(ah_tm + lane_base + 8 * kc, hi);
-        mt_tmem_st8(al_tm + lane_base + 8 * kc, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // A complete; the staged trajectories are dead from here on
-    float* prow = s_buf + tid * nb;
+    float* prow = s_buf + rr * nb;
     const float i2 = inv_s * inv_s;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -302,9 +319,10 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
       mt_mbar_wait(bar_a, parity);
       parity ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- |X|^2 of this thread's row, bins 32 h .. 32 h + 31, into the staging buffer (pitch nb, odd)
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      // ---- |X|^2 of this thread's row, bins 32 h + 16 q .. + 15 with q = the thread's half, into the staging buffer
+      // (pitch nb, odd)
+      {
+        const int q = half;
         float re0[16], re1[16], im0[16], im1[16];
         mt_tmem_ld16(d_tm + lane_base + 16 * q, re0);            // D0: hi . Ghi
         mt_tmem_ld16(d_tm + lane_base + 64 + 16 * q, re1);       // D1: hi . Glo + lo . Ghi
@@ -315,7 +333,7 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
         for (int j = 0; j < 16; ++j) {
           const float re = fmaf(re1[j], 1.0f / 2048.0f, re0[j]), im = fmaf(im1[j], 1.0f / 2048.0f, im0[j]);
           const int k = 32 * h + 16 * q + j;
-          if (h == 0 && q == 0 && j == 0) {
+          if (h == 0 && j == 0 && q == 0) {
             prow[0] = re * re * i2;
             prow[H] = im * im * i2;  // Re X[H] rides in the Im X[0] slot
           } else {
@@ -329,15 +347,18 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
         __syncthreads();
       }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // a row's |X|^2 values come from both of its threads
     {
       if (valid && p.n_bands > 0) {
-        for (int b = 0; b < p.n_bands; ++b) {
+        for (int b = half; b < p.n_bands; b += 2) {
           float e = 0.0f;
           for (int k = s_blo[b]; k < s_bhi[b]; ++k) e += prow[k];
           s_iband[((size_t)w * p.n_coef + coef) * p.n_bands + b] = e;
         }
       }
-      s_dst[tid] = (valid && p.mag != nullptr) ? p.mag + (((size_t)clip * p.n_coef + coef) * p.n_win + w0 + w) * nb : nullptr;
+      if (half == 0)
+        s_dst[rr] = (valid && p.mag != nullptr) ? p.mag + (((size_t)clip * p.n_coef + coef) * p.n_win + w0 + w) * nb : nullptr;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
       // the whole clip is one chunk: consecutive rows are consecutive output rows, the block is one flat
       // stream of min(128, n_items - r0) * nb floats
       float* dst = p.mag + (((size_t)clip * p.n_coef) * p.n_win + r0) * nb;
-      const int n_out = min(kMtThreads, n_items - r0) * nb;
+      const int n_out = min(kMtRows, n_items - r0) * nb;
 #pragma unroll 13
       for (int e = tid; e < n_out; e += kMtThreads) {
         float m;
@@ -354,14 +375,14 @@ __global__ void __launch_bounds__(kMtThreads) modspec_tc_kernel(const ModTcArgs 
         dst[e] = m;
       }
     } else if (p.mag != nullptr) {
-      // a warp writes its 32 rows one after the other, 65 consecutive floats per row; lane l holds row l's
-      // destination and hands it round by shuffle (no dependent shared-memory load per row)
+      // a warp writes its 16 rows one after the other, 65 consecutive floats per row; lane l (mod 16) holds row
+      // l's destination and hands it round by shuffle (no dependent shared-memory load per row)
       const int lane = tid & 31;
-      const unsigned long long mine = (unsigned long long)(uintptr_t)s_dst[warp * 32 + lane];
+      const unsigned long long mine = (unsigned long long)(uintptr_t)s_dst[warp * 16 + (lane & 15)];
 #pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        float* dst = reinterpret_cast<float*>((uintptr_t)__shfl_sync(0xffffffffu, mine, rr));
-        const float* src = s_buf + (warp * 32 + rr) * nb;
+      for (int q = 0; q < 16; ++q) {
+        float* dst = reinterpret_cast<float*>((uintptr_t)__shfl_sync(0xffffffffu, mine, q));
+        const float* src = s_buf + (warp * 16 + q) * nb;
         if (dst != nullptr) {
 #pragma unroll
           for (int k0 = 0; k0 < nb; k0 += 32) {
@@ -447,11 +468,11 @@ cudaError_t modspec_tc_launch(const float* mfcc, long n_clips, int n_coef, long 
   long wc = n_win;
   auto fits = [&](long w) {
     const long span = (w - 1) * hop + win;
-    const long n_tr = std::min<long>(n_coef, (kMtThreads - 1) / w + 2);
+    const long n_tr = std::min<long>(n_coef, (kMtRows - 1) / w + 2);
     // dynamic shared memory of a CTA: operand table + staging buffer + row pointers + band table, within the
     // 110 KB the kernel opts into (two CTAs per SM) less its static variables
-    const long fixed = 2L * nfft * kp * 2 + (long)kMtThreads * nb * 4 + (long)kMtThreads * (long)sizeof(float*);
-    return n_tr * span <= (long)kMtThreads * nb && fixed + w * n_coef * std::max(n_bands, 1) * 4 <= kMtSmemLimit - 512;
+    const long fixed = 2L * nfft * kp * 2 + (long)kMtRows * nb * 4 + (long)kMtRows * (long)sizeof(float*);
+    return n_tr * span <= (long)kMtRows * nb && fixed + w * n_coef * std::max(n_bands, 1) * 4 <= kMtSmemLimit - 2048;
   };
   while (wc > 1 && !fits(wc)) wc = (wc + 1) / 2;
   if (!fits(wc)) return cudaSuccess;
@@ -475,7 +496,7 @@ cudaError_t modspec_tc_launch(const float* mfcc, long n_clips, int n_coef, long 
   a.band_lo = lo;
   a.band_hi = hi;
   a.n_bands = n_bands;
-  const size_t smem = (size_t)2 * nfft * kp * 2 + (size_t)kMtThreads * nb * 4 + kMtThreads * sizeof(float*) +
+  const size_t smem = (size_t)2 * nfft * kp * 2 + (size_t)kMtRows * nb * 4 + kMtRows * sizeof(float*) +
                       (size_t)wc * n_coef * std::max(n_bands, 1) * 4;
 #define MMF_MT_CASE(KS)                                                            \
   case KS: {                                                                       \
