@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "mmf_internal.h"
@@ -247,44 +248,48 @@ __global__ void __launch_bounds__(kMtThreads, 2) modspec_tc_kernel(const ModTcAr
     const int w = valid ? r - coef * wca : 0;
     float inv_s = 1.0f;
     {
-      constexpr int KH = (KS + 1) / 2;          // slabs of half 0
-      constexpr int KL = KH;                    // slabs held per thread (half 1 may use one fewer)
-      const int ks0 = half == 0 ? 0 : KH, nks = half == 0 ? KH : KS - KH;
       const float* x = s_buf + (coef - c_lo) * pitch + w * p.hop;
-      float v[16 * KL];
-      // mean removal relative to a pivot (the window's first sample): the differences are small next to a
-      // trajectory's offset (c0 sits near -500), so the fp32 sum loses far less; four partial sums
-      // rows past the last item read row (c_lo, 0): finite data, results never stored
-      const float pivot = x[0];
-      float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      // the two halves as two instantiations: slab ranges and the tail predicate are compile-time in each (a warp
+      // lies in one half, so the branch is warp-uniform)
+      auto prepare = [&](auto half_tag) {
+        constexpr int HALF = decltype(half_tag)::value;
+        constexpr int KH = (KS + 1) / 2;                 // slabs of half 0
+        constexpr int K0 = HALF == 0 ? 0 : 16 * KH;      // first k of this half
+        constexpr int NK = HALF == 0 ? 16 * KH : 16 * (KS - KH);
+        float v[NK > 0 ? NK : 1];
+        // mean removal relative to a pivot (the window's first sample): the differences are small next to a
+        // trajectory's offset (c0 sits near -500), so the fp32 sum loses far less; four partial sums
+        // rows past the last item read row (c_lo, 0): finite data, results never stored.  win > 16 (KS - 1):
+        // only the last slab of the row needs the k < win predicate
+        const float pivot = x[0];
+        float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (int kl = 0; kl < 16 * KL; ++kl) {
-        const int k = 16 * ks0 + kl;
-        v[kl] = (kl < 16 * nks && k < p.win) ? x[k] - pivot : 0.0f;
-        sum4[kl & 3] += v[kl];
-      }
-      s_part[half][rr] = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      __syncthreads();
-      const float mean = (s_part[0][rr] + s_part[1][rr]) * inv_win;
-      __syncthreads();  // both halves have read the sums: the buffer takes the maxima
-      float m = 0.0f;
+        for (int kl = 0; kl < NK; ++kl) {
+          const int k = K0 + kl;
+          v[kl] = (k < 16 * KS - 16 || k < p.win) ? x[k] - pivot : 0.0f;
+          sum4[kl & 3] += v[kl];
+        }
+        s_part[HALF][rr] = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        __syncthreads();
+        const float mean = (s_part[0][rr] + s_part[1][rr]) * inv_win;
+        __syncthreads();  // both halves have read the sums: the buffer takes the maxima
+        float m = 0.0f;
 #pragma unroll
-      for (int kl = 0; kl < 16 * KL; ++kl) {
-        const int k = 16 * ks0 + kl;
-        v[kl] = (kl < 16 * nks && k < p.win) ? v[kl] - mean : 0.0f;
-        m = fmaxf(m, fabsf(v[kl]));
-      }
-      s_part[half][rr] = m;
-      __syncthreads();
-      m = fmaxf(s_part[0][rr], s_part[1][rr]);
-      int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
-      if (m < 1e-30f) e = 5;
-      e = max(-100, min(100, e));
-      const float s = __uint_as_float((uint32_t)(5 - e + 127) << 23);  // m s in [32, 64)
-      inv_s = __uint_as_float((uint32_t)(e - 5 + 127) << 23);
+        for (int kl = 0; kl < NK; ++kl) {
+          const int k = K0 + kl;
+          v[kl] = (k < 16 * KS - 16 || k < p.win) ? v[kl] - mean : 0.0f;
+          m = fmaxf(m, fabsf(v[kl]));
+        }
+        s_part[HALF][rr] = m;
+        __syncthreads();
+        m = fmaxf(s_part[0][rr], s_part[1][rr]);
+        int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
+        if (m < 1e-30f) e = 5;
+        e = max(-100, min(100, e));
+        const float s = __uint_as_float((uint32_t)(5 - e + 127) << 23);  // m s in [32, 64)
+        inv_s = __uint_as_float((uint32_t)(e - 5 + 127) << 23);
 #pragma unroll
-      for (int kc = 0; kc < KL; ++kc) {
-        if (kc < nks) {  // (warp-uniform: a warp lies in one half)
+        for (int kc = 0; kc < NK / 16; ++kc) {
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -295,11 +300,15 @@ __global__ void __launch_bounds__(kMtThreads, 2) modspec_tc_kernel(const ModTcAr
             hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
             lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-          mt_tmem_st8(ah_tm + lane_base + 8 * (ks0 + kc), hi);
-          mt_tmem_st8(al_tm + lane_base + 8 * (ks0 + kc), lo);
+          mt_tmem_st8(ah_tm + lane_base + K0 / 2 + 8 * kc, hi);
+          mt_tmem_st8(al_tm + lane_base + K0 / 2 + 8 * kc, lo);
         }
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      };
+      if (half == 0)
+        prepare(std::integral_constant<int, 0>{});
+      else
+        prepare(std::integral_constant<int, 1>{});
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // A complete; the staged trajectories are dead from here on
