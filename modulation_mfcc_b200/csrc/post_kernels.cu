@@ -116,20 +116,22 @@ __global__ void __launch_bounds__(kMfccThreads)
   }
 }
 
-// K3, fast form for n_mfcc <= 16 and n_mels a multiple of 8 (every BASELINE shape): same thread-per-frame layout and
+// K3, fast form for n_mfcc <= 32 and n_mels a multiple of 8 (every BASELINE shape; PITCH = padded table row: 16 or 32
+// coefficients): same thread-per-frame layout and
 // the same FMA order as mfcc_kernel (so the MFCCs are bit-identical), but coefficient PAIRS are accumulated with
 // packed FFMA2 (half the issue slots of the contraction), the mel rows are walked with pointer steps instead of
 // 64-bit index products, and the loop body carries no predicates.  ncu of mfcc_kernel<16> on the bench shape:
 // 83.4 M warp instructions of which 21 M are the FFMAs -- issue-bound at 95 us for a 271 MB stream.
-template <int NP>
+template <int NP, int PITCH>
 __global__ void __launch_bounds__(kMfccThreads)
     mfcc_pk_kernel(const float* __restrict__ dct_pad, float* logmel, const int* __restrict__ clipmax, long T, int n_mels,
                    int n_mfcc, float top_db, float* __restrict__ mfcc, float* __restrict__ delta, int clamp_in_place) {
   extern __shared__ __align__(16) float sm[];
-  float* s_dct = sm;                 // [n_mels][16]
-  float* s_col = sm + n_mels * 16;   // [2 NP][kMfccThreads + 1]
+  static_assert(2 * NP <= PITCH, "coefficient pairs must fit the padded table row");
+  float* s_dct = sm;                    // [n_mels][PITCH]
+  float* s_col = sm + n_mels * PITCH;   // [2 NP][kMfccThreads + 1]
   const int tid = threadIdx.x;
-  for (int i = tid; i < n_mels * 4; i += kMfccThreads)
+  for (int i = tid; i < n_mels * (PITCH / 4); i += kMfccThreads)
     reinterpret_cast<float4*>(s_dct)[i] = reinterpret_cast<const float4*>(dct_pad)[i];
   __syncthreads();
 
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kMfccThreads)
         const float x = fmaxf(cur[u], thr);
         if (store_clamped) col[u * Ti] = x;
         const pk xx = pmake(x, x);
-        const float4* d4 = reinterpret_cast<const float4*>(s_row + 16 * u);
+        const float4* d4 = reinterpret_cast<const float4*>(s_row + PITCH * u);
 #pragma unroll
         for (int j4 = 0; j4 < (NP + 1) / 2; ++j4) {
           const float4 d = d4[j4];
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kMfccThreads)
 #pragma unroll
       for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
       col = nrow;
-      s_row += 8 * 16;
+      s_row += 8 * PITCH;
     }
   }
   float out[2 * NP];
@@ -224,21 +226,30 @@ cudaError_t mfcc_launch(const float* dct_pad, int nc_pad, float* logmel, const i
   dim3 grid((unsigned)((T + per_block - 1) / per_block), (unsigned)n_clips);
   int nc = n_mfcc <= 16 ? 16 : (n_mfcc <= 32 ? 32 : (n_mfcc <= 64 ? 64 : 128));
   size_t smem = ((size_t)n_mels * nc + (size_t)nc * (kMfccThreads + 1)) * sizeof(float);
-  if (nc == 16 && nc_pad == 16 && n_mels % 8 == 0 && n_mels >= 8 && T < (1L << 27)) {
+  if ((nc == 16 || nc == 32) && nc_pad == nc && n_mels % 8 == 0 && n_mels >= 8 && T < (1L << 27)) {
     const int np = n_mfcc <= 8 ? 4 : (n_mfcc + 1) / 2;
-#define MMF_MFCC_PK_CASE(N)                                                                                        \
+#define MMF_MFCC_PK_CASE(N, P)                                                                                     \
   case N: {                                                                                                        \
-    MMF_SMEM_ONCE(mfcc_pk_kernel<N>, 200 * 1024);                                                                  \
-    mfcc_pk_kernel<N><<<grid, kMfccThreads, smem, st>>>(dct_pad, logmel, clipmax, T, n_mels, n_mfcc, top_db, mfcc, \
-                                                        delta, clamp_in_place);                                    \
+    auto kfn = mfcc_pk_kernel<N, P>;                                                                               \
+    MMF_SMEM_ONCE(kfn, 200 * 1024);                                                                                \
+    kfn<<<grid, kMfccThreads, smem, st>>>(dct_pad, logmel, clipmax, T, n_mels, n_mfcc, top_db, mfcc, delta,        \
+                                          clamp_in_place);                                                         \
     break;                                                                                                         \
   }
     switch (np) {
-      MMF_MFCC_PK_CASE(4)
-      MMF_MFCC_PK_CASE(5)
-      MMF_MFCC_PK_CASE(6)
-      MMF_MFCC_PK_CASE(7)
-      MMF_MFCC_PK_CASE(8)
+      MMF_MFCC_PK_CASE(4, 16)
+      MMF_MFCC_PK_CASE(5, 16)
+      MMF_MFCC_PK_CASE(6, 16)
+      MMF_MFCC_PK_CASE(7, 16)
+      MMF_MFCC_PK_CASE(8, 16)
+      MMF_MFCC_PK_CASE(9, 32)
+      MMF_MFCC_PK_CASE(10, 32)
+      MMF_MFCC_PK_CASE(11, 32)
+      MMF_MFCC_PK_CASE(12, 32)
+      MMF_MFCC_PK_CASE(13, 32)
+      MMF_MFCC_PK_CASE(14, 32)
+      MMF_MFCC_PK_CASE(15, 32)
+      MMF_MFCC_PK_CASE(16, 32)
     }
 #undef MMF_MFCC_PK_CASE
     count_launch();
